@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""Headline benchmark: batched negacyclic polymul, N = 4096, 60-bit modulus (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows R] [--config TAG]
+
+Own arm: one process per GPU (torchrun for N > 1).  The batch is sharded by rows, there is no
+data-path collective; torch.distributed only provides the barrier and the
+max-over-ranks reduction of the device time.  A "step" is one fused polymul launch over the
+rank's whole shard, inputs resident in HBM.  One JSON line is printed by rank 0.
+
+Reference arm (--impl reference): the reference's own C++ implementation of the path
+(software_benchmark/benchmark_ntt_60bit.cpp compiled unmodified into oracle/_ref) on all host
+threads, rank 0 only, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tiny-ntt_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "polymuls_per_sec_n4096_60bit"
+UNIT = "polymul/s"
+
+# workloads: tag -> rows per GPU (inputs exceed the 126 MB L2 in every case)
+ROWS = {"n4096_60": 1 << 15, "n4096_24": 1 << 16, "n1024_24": 1 << 18, "dilithium": 1 << 20}
+PARAMS = {
+    "dilithium": dict(n=256, q=8380417, psi=1239911),
+    "n1024_24": dict(n=1024, q=8380417, psi=5548360),
+    "n4096_24": dict(n=4096, q=8380417, psi=283817),
+    "n4096_60": dict(n=4096, q=(1 << 60) - (1 << 14) + 1, psi=431606828070683274),
+}
+# algorithmic work per polymul
+MODMULS = {256: 3584, 1024: 17408, 4096: 81920}
+IMAD_PER_MODMUL = {4: 3.0, 8: 10.05}   # u64: (73728*10 + 4096*11 + 4096*10) / 81920
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--config", default="n4096_60", choices=sorted(PARAMS))
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: workload table)")
+    ap.add_argument("--variant", type=int, default=-1, help="force a kernel variant (benchmarking)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_reference_throughput(tag: str, seconds: float = 10.0):
+    """polymul/s of the reference's own C++ code on all host threads, on a bounded sample."""
+    import numpy as np
+
+    from oracle.cpu_ref import COracle, RefLib, best_simd
+
+    p = PARAMS[tag]
+    cores = os.cpu_count() or 1
+    try:
+        affinity = len(os.sched_getaffinity(0))
+        cores = min(cores, affinity)
+    except AttributeError:
+        pass
+    rng = np.random.default_rng(1234)
+    if RefLib.available(tag):
+        lib = RefLib(tag)
+        kind, name = "reference", f"oracle/_ref/libref_{tag}_{lib.simd}.so (reference C++ sources, {lib.simd})"
+        run = lambda a, b: lib.polymul(a, b, threads=cores)          # noqa: E731
+        dt = lib.dtype
+    else:
+        co = COracle()
+        kind, name = "port", "oracle/ntt_oracle.c (C restatement)"
+        run = lambda a, b: co.nwc_poly_mult(a, b, p["psi"], p["q"], threads=cores)  # noqa: E731
+        dt = np.uint64
+    probe = max(cores * 2, 8)
+    a = rng.integers(0, p["q"], size=(probe, p["n"]), dtype=np.uint64).astype(dt)
+    b = rng.integers(0, p["q"], size=(probe, p["n"]), dtype=np.uint64).astype(dt)
+    run(a, b)
+    t = time.perf_counter()
+    run(a, b)
+    per_row = (time.perf_counter() - t) / probe
+    rows = int(max(probe, min(seconds / max(per_row, 1e-9), 1 << 17)))
+    a = rng.integers(0, p["q"], size=(rows, p["n"]), dtype=np.uint64).astype(dt)
+    b = rng.integers(0, p["q"], size=(rows, p["n"]), dtype=np.uint64).astype(dt)
+    return dict(run=run, a=a, b=b, rows=rows, cores=cores, kind=kind, name=name)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tag = args.config
+    ctx = cpu_reference_throughput(tag, seconds=max(1.0, min(8.0, 120.0 / max(1, args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        ctx["run"](ctx["a"], ctx["b"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx["run"](ctx["a"], ctx["b"])
+    dt = time.perf_counter() - t0
+    value = ctx["rows"] * args.steps / dt
+    p = PARAMS[tag]
+    sample = f"{ctx['rows']} polymuls per step on {ctx['cores']} host threads, {ctx['name']}"
+    line = {
+        "impl": "reference", "metric": METRIC if tag == "n4096_60" else f"polymuls_per_sec_{tag}", "value": value,
+        "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64" if p["q"] >> 32 else "u32", "data": "synthetic",
+        "config": {"workload": workload_name(tag), "rows_per_step": ctx["rows"], "host_threads": ctx["cores"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ctx["cores"], "kind": ctx["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(tag):
+    p = PARAMS[tag]
+    return (f"batched negacyclic polymul N={p['n']} q={p['q']} ({p['q'].bit_length()}-bit) psi={p['psi']} "
+            f"(forward NTT x2 -> pointwise -> inverse NTT), rows sharded across GPUs")
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import tntt
+    from tntt.shard import max_over_ranks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tag = args.config
+    p = PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    plan = tntt.get_plan(n, q, psi, True, local)
+    if args.variant >= 0:
+        plan.set_default_variant(args.variant)
+    variant_desc = dict(plan.variants()).get(plan.default_variant, "literal-schedule path")
+    rows = args.rows or ROWS[tag]
+    wb = plan.word_bytes
+
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    a = torch.randint(0, q, (rows, n), generator=gen, device="cuda", dtype=torch.int64).to(plan.dtype)
+    b = torch.randint(0, q, (rows, n), generator=gen, device="cuda", dtype=torch.int64).to(plan.dtype)
+    c = torch.empty_like(a)
+
+    # parity gate before any timing: row 0/1 = the C++ benchmark's LCG
+    # polynomials, whose product checksum is a golden constant of the reference
+    from oracle import ntt_oracle as O
+
+    npdt = np.uint32 if wb == 4 else np.uint64
+    sdt = np.int32 if wb == 4 else np.int64
+    a[0] = torch.from_numpy(np.array(O.make_poly(tag, 1), dtype=npdt).view(sdt)).cuda()
+    b[0] = torch.from_numpy(np.array(O.make_poly(tag, 2), dtype=npdt).view(sdt)).cuda()
+    tntt.polymul(plan, a, b, out=c)
+    torch.cuda.synchronize()
+    golden = {"dilithium": 16424788039373839479, "n1024_24": 15308795525113097448,
+              "n4096_24": 11303505593119465445, "n4096_60": 2710933653778106521}[tag]
+    got = O.checksum(tag, [int(v) for v in c[0].cpu().numpy().view(npdt)])
+    if got != golden:
+        raise SystemExit(f"parity gate failed: checksum {got} != reference {golden}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        tntt.polymul(plan, a, b, out=c)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        tntt.polymul(plan, a, b, out=c)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    total_rows = rows * world
+    value = total_rows * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point (pinned memory, H2D + kernel + D2H per step)
+    e2e = None
+    if not args.no_e2e:
+        e_rows = min(rows, 1 << 13) if tag == "n4096_60" else min(rows, (256 << 20) // (n * wb))
+        ha = a[:e_rows].cpu().pin_memory()
+        hb = b[:e_rows].cpu().pin_memory()
+        hc = torch.empty_like(ha).pin_memory()
+        tntt.polymul_host(plan, ha, hb, out=hc)
+        if not torch.equal(hc, c[:e_rows].cpu()):
+            raise SystemExit("e2e parity failed: host pipeline result differs from the device result")
+        e_steps = max(3, min(args.steps, 10))
+        barrier()
+        tt0 = time.perf_counter()
+        for _ in range(e_steps):
+            tntt.polymul_host(plan, ha, hb, out=hc)       # blocking: returns when hc is complete
+        torch.cuda.synchronize()
+        e_ms = max_over_ranks((time.perf_counter() - tt0) * 1e3)
+        bytes_row = n * wb
+        e2e = {"value": e_rows * world * e_steps / (e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": 2 * e_rows * bytes_row, "d2h_bytes_per_step": e_rows * bytes_row,
+               "rows_per_step_per_gpu": e_rows, "steps": e_steps, "ms_per_step": e_ms / e_steps,
+               "api": "tntt_polymul_host (pinned host buffers, 3-stream chunked H2D/kernel/D2H)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    launch_s = ms * 1e-3 / args.steps
+    alg_bytes = 3 * n * wb * rows                                  # read a, read b, write c (per launch, per GPU)
+    achieved = alg_bytes / launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh).get(tag)
+        if tj:
+            traffic = tj["dram_bytes_per_row"] * rows
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "kernel": variant_desc.split(" ")[0], "bytes_per_polymul": 3 * n * wb, "launch_ms": launch_s * 1e3}
+    # the binding ceiling is the integer pipe: measured IMAD issue rate
+    imad = None
+    try:
+        peak_wide = tntt.microbench(1, local)
+        peak_lo = tntt.microbench(0, local)
+        per_polymul = MODMULS[n] * IMAD_PER_MODMUL[wb]
+        ach = value / world * per_polymul
+        imad = {"bound": "imad", "achieved": ach / 1e12, "peak": max(peak_wide, peak_lo) / 1e12, "unit": "TIMAD32/s",
+                "frac": ach / max(peak_wide, peak_lo), "imad32_per_polymul": per_polymul,
+                "peak_source": "measured in this run: tntt_microbench IMAD.WIDE.U32 / IMAD.LO dependency-free chains",
+                "peak_imad_wide": peak_wide / 1e12, "peak_imad_lo": peak_lo / 1e12,
+                "shoup64_modmul_per_s": tntt.microbench(3, local), "shoup32_modmul_per_s": tntt.microbench(4, local)}
+    except Exception as exc:  # measurement aid only
+        imad = {"error": str(exc)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ctx = cpu_reference_throughput(tag, seconds=10.0)
+        t = time.perf_counter()
+        ctx["run"](ctx["a"], ctx["b"])
+        dt = time.perf_counter() - t
+        cpu = {"value": ctx["rows"] / dt, "unit": UNIT, "cores": ctx["cores"], "kind": ctx["kind"],
+               "sample": f"{ctx['rows']} polymuls of the same workload, {ctx['name']}, one pass after warm-up"}
+
+    line = {
+        "metric": METRIC if tag == "n4096_60" else f"polymuls_per_sec_{tag}", "value": value, "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64" if wb == 8 else "u32", "data": "synthetic",
+        "config": {"workload": workload_name(tag), "rows_per_gpu": rows, "rows_total": total_rows,
+                   "parallelism": f"batch-sharded x{world}, no collective", "kernel_variant": variant_desc,
+                   "l2": "inputs exceed L2 (%.2f GB read per launch vs 126 MB)" % (2 * n * wb * rows / 1e9)},
+        "roofline": roofline, "imad_roofline": imad, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,258 @@
+// CPU emulation of the CUDA kernels' thread/tile choreography.  TEST FIXTURE ONLY.
+//
+// Includes the very same __host__ __device__ building blocks the kernels are made of
+// (tiny-ntt_b200/csrc/kernels.cuh: index maps, swizzle, passes, arithmetic) and replays the
+// kernel bodies with "for every thread" loops between the __syncthreads() points.  This lets
+// the CPU-only test-suite (-m "not gpu") check index maps, tables and lazy-range arithmetic
+// bit-for-bit against the oracle without a GPU.  It is not part of the product library and is
+// never used as a fallback; it also records the shared-memory slots touched per warp
+// instruction so tests/test_layout.py can count bank conflicts.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../tiny-ntt_b200/csrc/kernels.cuh"
+#include "../tiny-ntt_b200/csrc/tables.h"
+
+using namespace tntt;
+
+namespace {
+
+template <class C, int NA, bool RED> struct Emu {
+    using W = typename C::W;
+    static constexpr int T = C::THREADS;
+    std::vector<W> tile;
+    std::vector<W> x;   // [T][NA][R]
+    std::vector<W> fa;  // [T][R]
+    PolymulTables<W> tb;
+    Mod<W> mod;
+    long long overflow_checks = 0;
+
+    W (&X(int t))[NA][C::R] { return *reinterpret_cast<W(*)[NA][C::R]>(&x[(size_t)t * NA * C::R]); }
+    W (&F(int t))[C::R] { return *reinterpret_cast<W(*)[C::R]>(&fa[(size_t)t * C::R]); }
+
+    template <int PASS> void forward_from() {
+        if constexpr (PASS < C::NPASS) {
+            if constexpr (PASS > 0) {
+                for (int a = 0; a < NA; ++a) {
+                    W *tl = tile.data() + (size_t)a * C::PPC * C::N;
+                    for (int t = 0; t < T; ++t)
+                        tile_write<C, C::fwd_lo(PASS - 1)>(X(t)[a], tl, t >> C::LOGP, t & (C::P - 1));
+                    for (int t = 0; t < T; ++t) {
+                        tile_read<C, C::fwd_lo(PASS)>(X(t)[a], tl, t >> C::LOGP, t & (C::P - 1));
+                        if (RED) reduce_top<C>(X(t)[a], mod);
+                    }
+                }
+            }
+            for (int t = 0; t < T; ++t) fwd_pass<C, PASS, NA>(X(t), t & (C::P - 1), tb, mod);
+            forward_from<PASS + 1>();
+        }
+    }
+    template <int PASS> void dit_from(const Tw<W> *pyr) {
+        if constexpr (PASS < C::NPASS) {
+            if constexpr (PASS > 0) {
+                for (int t = 0; t < T; ++t)
+                    tile_write<C, C::inv_lo(PASS - 1)>(F(t), tile.data(), t >> C::LOGP, t & (C::P - 1));
+                for (int t = 0; t < T; ++t) {
+                    tile_read<C, C::inv_lo(PASS)>(F(t), tile.data(), t >> C::LOGP, t & (C::P - 1));
+                    if (RED) reduce_top<C>(F(t), mod);
+                }
+            }
+            for (int t = 0; t < T; ++t) dit_pass<C, PASS>(F(t), t & (C::P - 1), pyr, mod);
+            dit_from<PASS + 1>(pyr);
+        }
+    }
+
+    void polymul(const W *a, const W *b, W *c, size_t batch) {
+        tile.assign((size_t)NA * C::PPC * C::N, 0);
+        x.assign((size_t)T * NA * C::R, 0);
+        fa.assign((size_t)T * C::R, 0);
+        const size_t ctas = (batch + C::PPC - 1) / C::PPC;
+        for (size_t cta = 0; cta < ctas; ++cta) {
+            auto off = [&](int t, bool &active) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                active = poly < batch;
+                return active ? poly * C::N : 0;
+            };
+            bool act;
+            if (NA == 1) {
+                for (int t = 0; t < T; ++t) { size_t o = off(t, act); row_load<C>(X(t)[0], a + o, t & (C::P - 1), act); }
+                forward_from<0>();
+                for (int t = 0; t < T; ++t) for (int k = 0; k < C::R; ++k) F(t)[k] = X(t)[0][k];
+                for (int t = 0; t < T; ++t) { size_t o = off(t, act); row_load<C>(X(t)[0], b + o, t & (C::P - 1), act); }
+                forward_from<0>();
+                for (int t = 0; t < T; ++t)
+                    for (int k = 0; k < C::R; ++k) {
+                        W u = F(t)[k], v = X(t)[0][k];
+                        if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
+                        F(t)[k] = mont_mul(u, v, mod);
+                    }
+            } else {
+                for (int t = 0; t < T; ++t) {
+                    size_t o = off(t, act);
+                    row_load<C>(X(t)[0], a + o, t & (C::P - 1), act);
+                    row_load<C>(X(t)[NA - 1], b + o, t & (C::P - 1), act);
+                }
+                forward_from<0>();
+                for (int t = 0; t < T; ++t)
+                    for (int k = 0; k < C::R; ++k) {
+                        W u = X(t)[0][k], v = X(t)[NA - 1][k];
+                        if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
+                        F(t)[k] = mont_mul(u, v, mod);
+                    }
+            }
+            dit_from<0>(tb.inv_pyr);
+            for (int t = 0; t < T; ++t) {
+                size_t o = off(t, act);
+                row_store_scaled<C>(F(t), c + o, t & (C::P - 1), act, tb.post, Tw<W>{0, 0}, mod);
+            }
+        }
+    }
+
+    // standalone transform kernel body (transform_kernel in kernels.cuh)
+    void transform(const W *in, W *out, size_t batch, const TransformTables<W> &tt) {
+        tile.assign((size_t)C::PPC * C::N, 0);
+        fa.assign((size_t)T * C::R, 0);
+        const size_t ctas = (batch + C::PPC - 1) / C::PPC;
+        for (size_t cta = 0; cta < ctas; ++cta) {
+            for (int t = 0; t < T; ++t) {
+                const int tid = t & (C::P - 1), pl = t >> C::LOGP;
+                const size_t poly = cta * C::PPC + pl;
+                const bool active = poly < batch;
+                const size_t o = active ? poly * C::N : 0;
+                row_load<C>(F(t), in + o, tid, active);
+                for (int k = 0; k < C::R; ++k) {
+                    const int e = (k << C::LOGP) + tid;
+                    if (tt.pre) F(t)[k] = shoup_mul(F(t)[k], ld_tw(&tt.pre[e]), mod.q);
+                    else if (tt.reduce_input) F(t)[k] = shoup_mul(F(t)[k], (W)1, mod.one_p, mod.q);
+                    tile[C::spos(pl * C::N + bitrev_n(e, C::LOGN))] = F(t)[k];
+                }
+            }
+            for (int t = 0; t < T; ++t) tile_read<C, 0>(F(t), tile.data(), t >> C::LOGP, t & (C::P - 1));
+            dit_from<0>(tt.pyr);
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                const bool active = poly < batch;
+                row_store_scaled<C>(F(t), out + (active ? poly * C::N : 0), t & (C::P - 1), active, tt.post,
+                                    tt.post_uniform, mod);
+            }
+        }
+    }
+};
+
+template <class C, int NA, bool RED>
+int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q, uint64_t psi) {
+    using W = typename C::W;
+    constexpr int BITS = WordTraits<W>::BITS;
+    if (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN)) return -2;
+    const uint64_t omega = host::mulmod(psi, psi, q);
+    auto fwd = host::fwd_pyramid<W>(psi, C::N, q);
+    auto last = host::fwd_last_table<W>(fwd, C::LOGN, C::LOGR);
+    auto inv = host::dit_pyramid<W>(host::modinv(omega, q), C::N, q);
+    const uint64_t scale = host::mulmod(host::modinv(C::N % q, q), (uint64_t)((((host::u128)1) << BITS) % q), q);
+    auto post = host::scaled_powers<W>(host::modinv(psi, q), scale, C::N, q);
+    Emu<C, NA, RED> e;
+    e.tb = PolymulTables<W>{fwd.data(), last.data(), inv.data(), post.data()};
+    e.mod = host::make_mod<W>(q);
+    e.polymul((const W *)a, (const W *)b, (W *)c, batch);
+    return 0;
+}
+
+// mode 0: cg_ntt (root = omega); 1: cg_intt; 2: twisted forward; 3: twisted inverse
+template <class C, bool RED>
+int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t root, int mode, int reduce_input) {
+    using W = typename C::W;
+    const bool inverse = mode & 1, twist = mode & 2;
+    const uint64_t omega = twist ? host::mulmod(root, root, q) : root;
+    auto pyr = host::dit_pyramid<W>(inverse ? host::modinv(omega, q) : omega, C::N, q);
+    std::vector<Tw<W>> pre, post;
+    const uint64_t n_inv = host::modinv(C::N % q, q);
+    if (twist && !inverse) pre = host::scaled_powers<W>(root, 1, C::N, q);
+    if (twist && inverse) post = host::scaled_powers<W>(host::modinv(root, q), n_inv, C::N, q);
+    TransformTables<W> tt;
+    tt.pyr = pyr.data();
+    tt.pre = pre.empty() ? nullptr : pre.data();
+    tt.post = post.empty() ? nullptr : post.data();
+    tt.post_uniform = host::make_tw<W>(inverse ? n_inv : 1, q);
+    tt.reduce_input = reduce_input;
+    Emu<C, 1, RED> e;
+    e.mod = host::make_mod<W>(q);
+    e.transform((const W *)in, (W *)out, batch, tt);
+    return 0;
+}
+
+}  // namespace
+
+#define POLY_CASE(WB, WT, LN, LR, PPC, NA_, RED_)                                                      \
+    if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && na == NA_ && red == RED_)       \
+        return run_polymul<Cfg<WT, LN, LR, PPC>, NA_, (RED_ != 0)>(a, b, c, batch, q, psi);
+#define XFORM_CASE(WB, WT, LN, LR, PPC, RED_)                                                          \
+    if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && red == RED_)                    \
+        return run_transform<Cfg<WT, LN, LR, PPC>, (RED_ != 0)>(in, out, batch, q, root, mode, reduce_input);
+
+extern "C" {
+
+int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, const void *a, const void *b, void *c,
+                size_t batch, uint64_t q, uint64_t psi) {
+    POLY_CASE(4, uint32_t, 2, 1, 2, 1, 0)
+    POLY_CASE(4, uint32_t, 4, 2, 4, 1, 0)
+    POLY_CASE(4, uint32_t, 5, 2, 2, 2, 0)
+    POLY_CASE(4, uint32_t, 8, 4, 16, 1, 0)
+    POLY_CASE(4, uint32_t, 8, 4, 16, 2, 0)
+    POLY_CASE(4, uint32_t, 8, 3, 8, 1, 0)
+    POLY_CASE(4, uint32_t, 10, 5, 8, 1, 0)
+    POLY_CASE(4, uint32_t, 10, 5, 8, 2, 0)
+    POLY_CASE(4, uint32_t, 10, 4, 4, 1, 0)
+    POLY_CASE(4, uint32_t, 10, 4, 4, 2, 0)
+    POLY_CASE(4, uint32_t, 12, 4, 1, 1, 0)
+    POLY_CASE(4, uint32_t, 12, 4, 1, 2, 0)
+    POLY_CASE(4, uint32_t, 12, 5, 2, 1, 0)
+    POLY_CASE(4, uint32_t, 12, 3, 1, 1, 0)
+    POLY_CASE(8, uint64_t, 8, 4, 16, 1, 0)
+    POLY_CASE(8, uint64_t, 8, 4, 16, 1, 1)
+    POLY_CASE(8, uint64_t, 10, 4, 4, 1, 0)
+    POLY_CASE(8, uint64_t, 10, 4, 4, 1, 1)
+    POLY_CASE(8, uint64_t, 12, 4, 1, 1, 0)
+    POLY_CASE(8, uint64_t, 12, 4, 1, 1, 1)
+    POLY_CASE(8, uint64_t, 12, 4, 1, 2, 1)
+    POLY_CASE(8, uint64_t, 12, 3, 1, 1, 1)
+    POLY_CASE(8, uint64_t, 12, 3, 1, 2, 1)
+    return -1;
+}
+
+int emu_transform(int word_bytes, int logn, int logr, int ppc, int red, const void *in, void *out, size_t batch,
+                  uint64_t q, uint64_t root, int mode, int reduce_input) {
+    XFORM_CASE(4, uint32_t, 4, 2, 4, 0)
+    XFORM_CASE(4, uint32_t, 8, 4, 16, 0)
+    XFORM_CASE(4, uint32_t, 10, 5, 8, 0)
+    XFORM_CASE(4, uint32_t, 10, 4, 4, 0)
+    XFORM_CASE(4, uint32_t, 12, 4, 1, 0)
+    XFORM_CASE(8, uint64_t, 8, 4, 16, 1)
+    XFORM_CASE(8, uint64_t, 12, 4, 1, 0)
+    XFORM_CASE(8, uint64_t, 12, 4, 1, 1)
+    XFORM_CASE(8, uint64_t, 12, 3, 1, 1)
+    return -1;
+}
+
+// shared-memory slot of (poly-in-cta, register k, thread tid) for a register field at bit `lo`
+int emu_slot(int word_bytes, int logn, int logr, int lo, int pl, int tid, int k) {
+    const int n = 1 << logn;
+    const int e = ((tid >> lo) << (lo + logr)) | (k << lo) | (tid & ((1 << lo) - 1));
+    const int E = pl * n + e;
+    const int mask = (1 << (word_bytes == 4 ? 5 : 4)) - 1;
+    return E ^ ((E >> logr) & mask);
+}
+
+// arithmetic probes for tests/test_modarith.py
+uint64_t emu_shoup64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_mul(x, t.w, t.wp, q); }
+uint32_t emu_shoup32(uint32_t x, uint32_t w, uint32_t q) { auto t = host::make_tw<uint32_t>(w, q); return shoup_mul(x, t.w, t.wp, q); }
+uint64_t emu_mont64(uint64_t x, uint64_t y, uint64_t q) { return mont_mul(x, y, host::make_mod<uint64_t>(q)); }
+uint32_t emu_mont32(uint32_t x, uint32_t y, uint32_t q) { return mont_mul(x, y, host::make_mod<uint32_t>(q)); }
+uint64_t emu_barrett64(uint64_t x, uint64_t y, uint64_t q) { return barrett_mul(x, y, host::make_mod<uint64_t>(q)); }
+uint32_t emu_barrett32(uint32_t x, uint32_t y, uint32_t q) { return barrett_mul(x, y, host::make_mod<uint32_t>(q)); }
+uint64_t emu_csub_top64(uint64_t x, uint64_t q) { return csub_top(x, host::make_mod<uint64_t>(q).top_sub); }
+int emu_is_prime(uint64_t n) { return host::is_prime(n); }
+int emu_lazy_full_ok(int word_bytes, uint64_t q, int logn) {
+    return word_bytes == 4 ? host::lazy_full_ok<uint32_t>(q, logn) : host::lazy_full_ok<uint64_t>(q, logn);
+}
+}

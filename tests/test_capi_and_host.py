@@ -1,0 +1,160 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/tntt.h declares, the
+host-side mirror raises the reference's errors, there is no CPU fallback, sharding logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "tntt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tntt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import tntt
+
+    assert os.path.exists(tntt.LIB_PATH), "build libtntt.so first (python -c 'import __graft_entry__ as g; g.build()')"
+    L = ctypes.CDLL(tntt.LIB_PATH)
+    declared = header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/tntt.h but not exported"
+    assert sorted(tntt.SYMBOLS) == declared, "python binding and header disagree"
+    assert tntt.lib().tntt_version() == 100
+    # nothing but the C ABI leaks out of the shared object
+    out = subprocess.check_output(["nm", "-D", "--defined-only", tntt.LIB_PATH], text=True)
+    exported = sorted(line.split()[-1] for line in out.splitlines() if " T " in line)
+    assert [e for e in exported if e.startswith("tntt_")] == declared
+    assert not [e for e in exported if not e.startswith("tntt_") and not e.startswith("_")]
+
+
+def test_library_contains_sm100a_code_only():
+    import tntt
+
+    out = subprocess.run(["cuobjdump", "-lelf", tntt.LIB_PATH], capture_output=True, text=True).stdout
+    if not out.strip():
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+
+    import cg_ntt
+    import tntt
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cg_ntt.nwc_poly_mult([0] * 256, [0] * 256, 1239911)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cg_ntt.cg_ntt([0] * 256, 5)
+    h = ctypes.c_void_p()
+    rc = tntt.lib().tntt_plan_create(ctypes.byref(h), 0, 256, 8380417, 1239911, 1)
+    assert rc == -7 and b"no CPU path" in tntt.lib().tntt_last_error()      # TNTT_NO_DEVICE
+    v = ctypes.c_double()
+    assert tntt.lib().tntt_microbench(0, 0, ctypes.byref(v)) == -7
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tiny-ntt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("no oracle", ""), f"{f} mentions the oracle"
+                assert "/root/reference" not in text, f
+
+
+def test_reference_error_behaviour_on_the_host_side():
+    import cg_ntt
+    import cg_ntt_8butterfly as m8
+
+    assert (cg_ntt.N, cg_ntt.Q) == (256, 8380417)
+    with pytest.raises(ValueError, match=r"^Expected 256 coefficients, got 3$"):
+        cg_ntt.cg_ntt([1, 2, 3], 5)
+    with pytest.raises(ValueError, match=r"^Expected 256 coefficients, got 0$"):
+        cg_ntt.cg_intt([], 5)
+    with pytest.raises(ValueError, match=r"^Expected 256 coefficients$"):
+        cg_ntt.nwc_poly_mult([0] * 255, [0] * 256, 7)
+    with pytest.raises(ValueError, match=r"^Expected 8 butterfly lanes$"):
+        m8.butterfly_batch([0] * 8, [0] * 7, [0] * 8)
+    with pytest.raises(ValueError, match=r"^Expected 256 coefficients, got 2$"):
+        m8.cg_ntt_8butterfly([1, 2], 5)
+    saved = cg_ntt.N
+    try:
+        cg_ntt.N = 1024                      # module globals are read at call time (cg_ntt.py:36)
+        with pytest.raises(ValueError, match=r"^Expected 1024 coefficients, got 256$"):
+            cg_ntt.cg_ntt([0] * 256, 5)
+    finally:
+        cg_ntt.N = saved
+    assert cg_ntt.modinv(256) == 8347681 and cg_ntt.modinv(3, 7) == 5
+    assert cg_ntt.bit_reverse(1, 8) == 128 and cg_ntt.bit_reverse(6, 3) == 3
+    assert cg_ntt.bit_reverse_list(list(range(8))) == [0, 4, 2, 6, 1, 5, 3, 7]
+    assert m8.N == 256 and m8.modinv is cg_ntt.modinv
+
+
+def test_shard_ranges_cover_the_batch_exactly():
+    from tntt.shard import shard_range
+
+    for total in (0, 1, 7, 8, 9, 4096, 32768 + 5):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) == -(-total // world) if total else max(sizes) == 0
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tiny-ntt_b200"))
+import numpy as np, torch, torch.distributed as dist
+from tntt.shard import shard_range, shard_rows, max_over_ranks, sum_over_ranks
+from oracle.cpu_ref import COracle
+from oracle import ntt_oracle as O
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+p = O.PARAMS["dilithium"]; n, q, psi = p["n"], p["q"], p["psi"]
+rng = np.random.default_rng(99)                      # same global batch on both ranks
+a = rng.integers(0, q, size=(11, n), dtype=np.uint64); b = rng.integers(0, q, size=(11, n), dtype=np.uint64)
+mine_a, mine_b = shard_rows(a, 2, rank), shard_rows(b, 2, rank)
+lo, hi = shard_range(11, 2, rank)
+assert mine_a.shape[0] == hi - lo == (6 if rank == 0 else 5)
+# each rank computes ITS rows only (the oracle stands in for the GPU kernel here); no data-path collective
+mine_c = COracle().nwc_poly_mult(mine_a, mine_b, psi, q)
+full = COracle().nwc_poly_mult(a, b, psi, q)
+assert (mine_c == full[lo:hi]).all()
+# bench.py's timing reduction: max over ranks of the per-rank device time, sum of rows
+assert max_over_ranks(1.0 + rank) == 2.0
+assert sum_over_ranks(hi - lo) == 11.0
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharded_batches_with_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o

@@ -1,0 +1,137 @@
+"""The kernels' index maps, tables and lazy arithmetic, executed on the CPU (tests/host_emul.cpp
+replays the kernel bodies from the same __host__ __device__ code) and compared with the oracle."""
+import random
+
+import numpy as np
+import pytest
+
+import emu
+from oracle import ntt_oracle as O
+from oracle.cpu_ref import COracle
+
+#        word logn logr ppc na red tag
+POLY = [(4, 8, 4, 16, 1, 0, "dilithium"), (4, 8, 4, 16, 2, 0, "dilithium"), (4, 8, 3, 8, 1, 0, "dilithium"),
+        (4, 10, 5, 8, 1, 0, "n1024_24"), (4, 10, 5, 8, 2, 0, "n1024_24"), (4, 10, 4, 4, 1, 0, "n1024_24"),
+        (4, 10, 4, 4, 2, 0, "n1024_24"), (4, 12, 4, 1, 1, 0, "n4096_24"), (4, 12, 4, 1, 2, 0, "n4096_24"),
+        (4, 12, 5, 2, 1, 0, "n4096_24"), (4, 12, 3, 1, 1, 0, "n4096_24"),
+        (8, 12, 4, 1, 1, 1, "n4096_60"), (8, 12, 4, 1, 2, 1, "n4096_60"), (8, 12, 3, 1, 1, 1, "n4096_60"),
+        (8, 12, 3, 1, 2, 1, "n4096_60"), (8, 12, 4, 1, 1, 0, "n4096_24"), (8, 8, 4, 16, 1, 0, "dilithium"),
+        (8, 8, 4, 16, 1, 1, "dilithium"), (8, 10, 4, 4, 1, 0, "n1024_24"), (8, 10, 4, 4, 1, 1, "n1024_24")]
+
+
+@pytest.fixture(scope="module")
+def co():
+    return COracle()
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,na,red,tag", POLY)
+def test_emulated_polymul_matches_oracle(wb, logn, logr, ppc, na, red, tag, co):
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    rng = np.random.default_rng(logn * 100 + logr * 10 + na)
+    batch = ppc + 3  # ragged: the last CTA is partly empty
+    a = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    a[0], b[0] = O.make_poly(tag, 1), O.make_poly(tag, 2)
+    a[1], b[1] = q - 1, q - 1          # largest canonical values: worst case for the lazy ranges
+    a[2], b[2] = 0, q - 1
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    got = emu.polymul(wb, logn, logr, ppc, na, red, a, b, q, psi).astype(np.uint64)
+    assert (got == want).all()
+
+
+def test_emulated_tiny_sizes(co):
+    # n = 4 worked example (test/refs/fast_ntt_negacyclic_convolution.py:161-214) and n = 16, 32
+    got = emu.polymul(4, 2, 1, 2, 1, 0, [[1, 2, 3, 4]], [[5, 6, 7, 8]], 7681, 1925)
+    assert got.tolist() == [[7625, 7645, 2, 60]]
+    q = 8380417
+    for logn, logr, ppc, na in ((4, 2, 4, 1), (5, 2, 2, 2)):
+        n = 1 << logn
+        psi = pow(1239911, 256 // n, q)
+        rng = np.random.default_rng(n)
+        a = rng.integers(0, q, size=(5, n), dtype=np.uint64)
+        b = rng.integers(0, q, size=(5, n), dtype=np.uint64)
+        got = emu.polymul(4, logn, logr, ppc, na, 0, a, b, q, psi).astype(np.uint64)
+        assert (got == co.nwc_poly_mult(a, b, psi, q)).all()
+
+
+XF = [(4, 8, 4, 16, 0, "dilithium"), (4, 10, 5, 8, 0, "n1024_24"), (4, 10, 4, 4, 0, "n1024_24"),
+      (4, 12, 4, 1, 0, "n4096_24"), (8, 8, 4, 16, 1, "dilithium"), (8, 12, 4, 1, 0, "n4096_24"),
+      (8, 12, 4, 1, 1, "n4096_60"), (8, 12, 3, 1, 1, "n4096_60")]
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,red,tag", XF)
+def test_emulated_transforms_match_oracle(wb, logn, logr, ppc, red, tag, co):
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    omega = psi * psi % q
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, q, size=(ppc + 1, n), dtype=np.uint64)
+    x[0] = q - 1
+    fwd = emu.transform(wb, logn, logr, ppc, red, x, q, omega, 0).astype(np.uint64)
+    assert (fwd == co.cg_ntt(x, omega, q)).all()                         # cg_ntt
+    inv = emu.transform(wb, logn, logr, ppc, red, x, q, omega, 1).astype(np.uint64)
+    assert (inv == co.cg_intt(x, omega, q)).all()                        # cg_intt
+    back = emu.transform(wb, logn, logr, ppc, red, fwd, q, omega, 1).astype(np.uint64)
+    assert (back == x).all()                                             # round trip
+    tw = emu.transform(wb, logn, logr, ppc, red, x[:1], q, psi, 2).astype(np.uint64)
+    assert tw[0].tolist() == O.forward_negacyclic([int(v) for v in x[0]], psi, q)   # ntt(twist(a))
+    rt = emu.transform(wb, logn, logr, ppc, red, tw, q, psi, 3).astype(np.uint64)
+    assert (rt == x[:1]).all()                                           # untwist(intt(...))
+
+
+def test_emulated_reduce_input_flag():
+    q = 8380417
+    omega = pow(1239911, 2, q)
+    rng = np.random.default_rng(9)
+    raw = rng.integers(0, 2**32, size=(2, 256), dtype=np.uint64)
+    got = emu.transform(4, 8, 4, 16, 0, raw, q, omega, 0, reduce_input=1)
+    want = [O.cg_ntt([int(v) for v in row], omega, q) for row in raw]
+    assert got.tolist() == want
+
+
+def test_modular_arithmetic_primitives():
+    L = emu.lib()
+    rnd = random.Random(3)
+    q60, q24 = O.PARAMS["n4096_60"]["q"], 8380417
+    r64, r32 = pow(2, 64, q60), pow(2, 32, q24)
+    for _ in range(20000):
+        x, w = rnd.getrandbits(64), rnd.randrange(q60)
+        t = L.emu_shoup64(x, w, q60)
+        assert t < 2 * q60 and t % q60 == x * w % q60            # any 64-bit x -> [0, 2q)
+        a, b = rnd.randrange(1 << 63), rnd.randrange(1 << 63)
+        m = L.emu_mont64(a, b, q60)
+        assert m < (1 << 62) + q60 and m * r64 % q60 == a * b % q60
+        c, d = rnd.randrange(q60), rnd.randrange(q60)
+        assert L.emu_barrett64(c, d, q60) == c * d % q60         # rtl/barrett_reduction.v formula
+        v = rnd.getrandbits(64)
+        s = L.emu_csub_top64(v, q60)
+        assert s % q60 == v % q60 and s < (1 << 63) + q60 * 8
+        x, w = rnd.getrandbits(32), rnd.randrange(q24)
+        t = L.emu_shoup32(x, w, q24)
+        assert t < 2 * q24 and t % q24 == x * w % q24
+        a, b = rnd.randrange(25 * q24), rnd.randrange(25 * q24)
+        m = L.emu_mont32(a, b, q24)
+        assert m * r32 % q24 == a * b % q24 and m < 3 * q24
+        c, d = rnd.randrange(q24), rnd.randrange(q24)
+        assert L.emu_barrett32(c, d, q24) == c * d % q24
+    assert L.emu_barrett64(q60 - 1, q60 - 1, q60) == (q60 - 1) ** 2 % q60
+    assert L.emu_barrett32(q24 - 1, q24 - 1, q24) == (q24 - 1) ** 2 % q24
+    # other moduli exercise the general shifts
+    for q in (7681, 12289, 65537, 2013265921, 4611686018326724609 >> 3 | 1):
+        k = q.bit_length()
+        for _ in range(2000):
+            c, d = rnd.randrange(q), rnd.randrange(q)
+            assert L.emu_barrett64(c, d, q) == c * d % q
+
+
+def test_host_number_theory_helpers():
+    L = emu.lib()
+    for p in (2, 3, 7681, 8380417, 1152921504606830593, 2013265921):
+        assert L.emu_is_prime(p)
+    for c in (1, 9, 8380417 * 3, 1152921504606830593 - 2, 2**59):
+        assert not L.emu_is_prime(c)
+    assert L.emu_lazy_full_ok(4, 8380417, 12) == 1            # Dilithium modulus runs reduction-free in 32 bits
+    assert L.emu_lazy_full_ok(4, (1 << 30) - 35, 12) == 0
+    assert L.emu_lazy_full_ok(8, 1152921504606830593, 12) == 0  # the 60-bit modulus needs the per-pass reduction
+    assert L.emu_lazy_full_ok(8, (1 << 50) - 27, 12) == 1

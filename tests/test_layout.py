@@ -1,0 +1,54 @@
+"""Shared-memory tile layout: every warp-wide access pattern the kernels use must be
+bank-conflict free (rtl/ntt_coeff_banks.v's banking constraint, re-expressed for 32 banks x 4 B)."""
+import pytest
+
+import emu
+
+#        word logn logr ppc   register-field positions used (forward and inverse passes)
+GEOMS = [(4, 8, 4, 16, (4, 0)), (4, 10, 5, 8, (5, 0)), (4, 10, 4, 4, (6, 2, 0, 4)), (4, 12, 4, 1, (8, 4, 0)),
+         (4, 12, 5, 2, (7, 2, 0, 5)), (4, 12, 3, 1, (9, 6, 3, 0)),
+         (8, 12, 4, 1, (8, 4, 0)), (8, 12, 3, 1, (9, 6, 3, 0)), (8, 8, 4, 16, (4, 0)), (8, 10, 4, 4, (6, 2, 0, 4))]
+
+
+def wavefronts(wb, slots):
+    """Number of shared-memory wavefronts a warp request needs: 4-byte words are served 32 lanes
+    at a time, 8-byte words 16 lanes at a time; a wavefront serves one address per bank."""
+    group = 32 if wb == 4 else 16
+    total = 0
+    for g in range(0, 32, group):
+        banks = {}
+        for s in slots[g:g + group]:
+            for word in range(wb // 4):
+                banks.setdefault((s * (wb // 4) + word) % 32, set()).add(s)
+        total += max(len(v) for v in banks.values())
+    return total
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,fields", GEOMS)
+def test_tile_accesses_are_conflict_free(wb, logn, logr, ppc, fields):
+    L = emu.lib()
+    p = 1 << (logn - logr)
+    threads = p * ppc
+    ideal = 1 if wb == 4 else 2
+    for lo in fields:
+        for warp in range(0, threads, 32):
+            for k in range(1 << logr):
+                slots = [L.emu_slot(wb, logn, logr, lo, t >> (logn - logr), t & (p - 1), k)
+                         for t in range(warp, min(warp + 32, threads))]
+                assert len(set(slots)) == len(slots)
+                if len(slots) == 32:
+                    assert wavefronts(wb, slots) == ideal, (lo, warp, k)
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,fields", GEOMS)
+def test_tile_slot_map_is_a_bijection(wb, logn, logr, ppc, fields):
+    L = emu.lib()
+    p = 1 << (logn - logr)
+    n = 1 << logn
+    for lo in fields:
+        seen = set()
+        for pl in range(ppc):
+            for t in range(p):
+                for k in range(1 << logr):
+                    seen.add(L.emu_slot(wb, logn, logr, lo, pl, t, k))
+        assert seen == set(range(ppc * n))

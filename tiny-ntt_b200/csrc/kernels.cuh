@@ -1,0 +1,338 @@
+// Per-thread building blocks of the batched NTT kernels (sm_100a).
+//
+// How the reference's hardware dataflow is re-expressed:
+//   rtl/ntt_cg_address_gen.v:57-117 + rtl/ntt_coeff_banks.v:159-320 (constant-geometry
+//   addressing over ping-pong banks, bit-reversal on load)
+//        -> a polynomial is held by P = N/R threads, R coefficients each, in registers.
+//           log2(R) butterfly stages run register-to-register; between such "passes" the
+//           coefficients are regrouped through an XOR-swizzled shared-memory tile
+//           (elem()/spos() below), which is bank-conflict free for every access pattern
+//           used (tests/test_layout.py enumerates them).
+//   rtl/twiddle_bram_multiport.v:21-66 -> twiddle+Shoup pairs read through the read-only
+//           path; tables are laid out so that a warp's request is contiguous or a broadcast.
+//   rtl/ntt_control_parallel.v:58-138 -> fully unrolled stage loops; __syncthreads() is the
+//           STAGE_DRAIN.
+//   rtl/ntt_pointwise_mult.v:17-42 -> pointwise product on registers between the last forward
+//           and first inverse pass (same thread<->coefficient layout), no memory traffic.
+//
+// Two transforms are used:
+//   fwd_pass : merged-psi Cooley-Tukey, natural order in -> bit-reversed order out
+//              (the psi^i twist of new_reference/cg_ntt.py:82-83 is folded into the twiddles)
+//   dit_pass : cyclic decimation-in-time with omega^-1 (or any root), bit-reversed in -> natural out;
+//              psi^-i * N^-1 (cg_ntt.py:74,91-92) is one multiply at the store.
+// Everything here is __host__ __device__ and takes the thread id as an argument so that
+// tests/host_emul.cpp can run the very same code on the CPU.
+#pragma once
+#include "modarith.cuh"
+
+namespace tntt {
+
+#if defined(__CUDACC__)
+#define TNTT_CX __host__ __device__ constexpr
+#else
+#define TNTT_CX constexpr
+#endif
+TNTT_CX int cmax(int a, int b) { return a > b ? a : b; }
+TNTT_CX int cmin(int a, int b) { return a < b ? a : b; }
+
+// Geometry of one kernel variant: W word, N = 2^LOGN coefficients, R = 2^LOGR per thread,
+// PPC polynomials per CTA, NA operands transformed side by side (sharing twiddle loads).
+template <typename W_, int LOGN_, int LOGR_, int PPC_> struct Cfg {
+    using W = W_;
+    static constexpr int LOGN = LOGN_, LOGR = LOGR_, N = 1 << LOGN, R = 1 << LOGR;
+    static constexpr int LOGP = LOGN - LOGR, P = 1 << LOGP;  // threads per polynomial
+    static constexpr int PPC = PPC_, THREADS = P * PPC;
+    static constexpr int NPASS = (LOGN + LOGR - 1) / LOGR;
+    static constexpr int BANK_MASK = (1 << WordTraits<W>::BANK_BITS) - 1;
+    static_assert(LOGN >= LOGR, "a thread cannot hold more than the polynomial");
+    // forward pass p works on index bits [fwd_lo(p), fwd_bhi(p)), high bits first
+    static TNTT_CX int fwd_lo(int p) { return cmax(LOGN - (p + 1) * LOGR, 0); }
+    static TNTT_CX int fwd_bhi(int p) { return LOGN - p * LOGR; }
+    // inverse (DIT) pass p works on index bits [inv_blo(p), inv_bhi(p)), low bits first;
+    // its register field starts at inv_lo(p)
+    static TNTT_CX int inv_lo(int p) { return cmin(p * LOGR, LOGN - LOGR); }
+    static TNTT_CX int inv_blo(int p) { return p * LOGR; }
+    static TNTT_CX int inv_bhi(int p) { return cmin((p + 1) * LOGR, LOGN); }
+    // coefficient index held in register k of thread tid when the register field sits at bit LO
+    template <int LO> static TNTT_HD int elem(int tid, int k) {
+        return ((tid >> LO) << (LO + LOGR)) | (k << LO) | (tid & ((1 << LO) - 1));
+    }
+    // shared-memory slot of CTA-wide element index E (= poly_in_cta * N + coefficient index)
+    static TNTT_HD int spos(int E) { return E ^ ((E >> LOGR) & BANK_MASK); }
+    // size of the transposed last-forward-pass twiddle table
+    static constexpr int FWD_LAST_ENTRIES = (R - 1) * P;
+};
+
+// Device view of the tables of one plan for one kernel variant.
+template <typename W> struct PolymulTables {
+    const Tw<W> *fwd_pyr;   // [N]  psi^bitrev pyramid: entry m+i, m = 2^stage
+    const Tw<W> *fwd_last;  // [(R-1)*P] the same values for the last forward pass, [slot][tid]
+    const Tw<W> *inv_pyr;   // [N]  omega^-1 DIT pyramid: entry t+j = omega^(-j*N/(2t))
+    const Tw<W> *post;      // [N]  psi^-i * N^-1 * 2^BITS (the 2^BITS undoes the Montgomery pointwise product)
+};
+template <typename W> struct TransformTables {
+    const Tw<W> *pyr;   // [N] DIT pyramid of the root (omega or omega^-1)
+    const Tw<W> *pre;   // [N] multiply on load (psi^i) or nullptr
+    const Tw<W> *post;  // [N] multiply on store (psi^-i N^-1) or nullptr -> post_uniform
+    Tw<W> post_uniform; // {1, floor(2^BITS/q)} (forward) or {N^-1, ...} (inverse)
+    int reduce_input;   // inputs may be any word: reduce on load
+};
+
+template <typename W> TNTT_HD Tw<W> ld_tw(const Tw<W> *p) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(W) == 4) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        return Tw<W>{v.x, v.y};
+    } else {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+        return Tw<W>{v.x, v.y};
+    }
+#else
+    return *p;
+#endif
+}
+template <typename W> TNTT_HD W ld_stream(const W *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcs(p);  // coefficients are touched once: evict-first, keeps the twiddles cached
+#else
+    return *p;
+#endif
+}
+template <typename W> TNTT_HD void st_stream(W *p, W v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// merged-psi Cooley-Tukey pass (natural -> bit-reversed), NA operands sharing each twiddle
+// ---------------------------------------------------------------------------------------------
+// one stage (index bit B) of a forward pass; B is a template parameter so that every loop bound
+// below is a compile-time constant and the register arrays never fall into local memory
+template <class C, int PASS, int NA, int B>
+TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
+                       const Mod<typename C::W> &mod) {
+    using W = typename C::W;
+    constexpr int LO = C::fwd_lo(PASS);
+    constexpr int kb = B - LO;            // bit of the register index this stage pairs over
+    constexpr int s = C::LOGN - 1 - B;    // stage number: 2^s blocks
+    constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        Tw<W> t;
+        if constexpr (LO == 0)  // last pass: every thread has its own twiddles -> transposed table, coalesced
+            t = ld_tw(&tb.fwd_last[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
+        else                    // earlier passes: uniform or shared by 2^LO consecutive threads -> broadcast
+            t = ld_tw(&tb.fwd_pyr[(1 << s) + ((tid >> LO) << (C::LOGR - 1 - kb)) + g]);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
+#pragma unroll
+            for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], t, mod);
+        }
+    }
+    if constexpr (B > LO) fwd_stage<C, PASS, NA, B - 1>(x, tid, tb, mod);
+}
+template <class C, int PASS, int NA>
+TNTT_HD void fwd_pass(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
+                      const Mod<typename C::W> &mod) {
+    fwd_stage<C, PASS, NA, C::fwd_bhi(PASS) - 1>(x, tid, tb, mod);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
+// ---------------------------------------------------------------------------------------------
+template <class C, int PASS, int B>
+TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const Tw<typename C::W> *pyr, const Mod<typename C::W> &mod) {
+    using W = typename C::W;
+    constexpr int LO = C::inv_lo(PASS);
+    constexpr int kb = B - LO;
+    constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const Tw<W> t = ld_tw(&pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
+            ct_butterfly(x[k0], x[k1], t, mod);
+        }
+    }
+    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, B + 1>(x, tid, pyr, mod);
+}
+template <class C, int PASS>
+TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const Tw<typename C::W> *pyr, const Mod<typename C::W> &mod) {
+    dit_stage<C, PASS, C::inv_blo(PASS)>(x, tid, pyr, mod);
+}
+
+template <class C> TNTT_HD void reduce_top(typename C::W (&x)[C::R], const Mod<typename C::W> &mod) {
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) x[k] = csub_top(x[k], mod.top_sub);
+}
+
+// registers -> swizzled tile (layout with the register field at LO)
+template <class C, int LO> TNTT_HD void tile_write(const typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid) {
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) tile[C::spos(pl * C::N + C::template elem<LO>(tid, k))] = x[k];
+}
+template <class C, int LO> TNTT_HD void tile_read(typename C::W (&x)[C::R], const typename C::W *tile, int pl, int tid) {
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) x[k] = tile[C::spos(pl * C::N + C::template elem<LO>(tid, k))];
+}
+
+TNTT_HD int bitrev_n(int v, int bits) {
+#if defined(__CUDA_ARCH__)
+    return (int)(__brev((unsigned)v) >> (32 - bits));
+#else
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+// coalesced row access: register k of thread tid <-> coefficient k*P + tid (field at LOGP)
+template <class C> TNTT_HD void row_load(typename C::W (&x)[C::R], const typename C::W *row, int tid, bool active) {
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) x[k] = active ? ld_stream(row + (k << C::LOGP) + tid) : (typename C::W)0;
+}
+
+// final multiply (psi^-i N^-1 ...) + canonical reduction + coalesced store
+template <class C>
+TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row, int tid, bool active,
+                              const Tw<typename C::W> *post, const Tw<typename C::W> &post_uniform,
+                              const Mod<typename C::W> &mod) {
+    using W = typename C::W;
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) {
+        const int e = (k << C::LOGP) + tid;
+        const Tw<W> t = post ? ld_tw(&post[e]) : post_uniform;
+        const W v = csub(shoup_mul(x[k], t.w, t.wp, mod.q), mod.q);
+        if (active) st_stream(row + e, v);
+    }
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------
+// regroup registers through the shared tile: layout LO_FROM -> LO_TO
+// ---------------------------------------------------------------------------------------------
+template <class C, int LO_FROM, int LO_TO>
+__device__ __forceinline__ void exchange(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid) {
+    __syncthreads();  // everybody is done reading the tile's previous contents
+    tile_write<C, LO_FROM>(x, tile, pl, tid);
+    __syncthreads();
+    tile_read<C, LO_TO>(x, tile, pl, tid);
+}
+
+template <class C, int NA, bool RED, int PASS = 0>
+__device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typename C::W *tile, int pl, int tid,
+                                            const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod) {
+    if constexpr (PASS < C::NPASS) {
+        if constexpr (PASS > 0) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                exchange<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[a], tile + a * C::PPC * C::N, pl, tid);
+                if (RED) reduce_top<C>(x[a], mod);
+            }
+        }
+        fwd_pass<C, PASS, NA>(x, tid, tb, mod);
+        forward_all<C, NA, RED, PASS + 1>(x, tile, pl, tid, tb, mod);
+    }
+}
+
+template <class C, bool RED, int PASS = 0>
+__device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid,
+                                        const Tw<typename C::W> *pyr, const Mod<typename C::W> &mod) {
+    if constexpr (PASS < C::NPASS) {
+        if constexpr (PASS > 0) {
+            exchange<C, C::inv_lo(PASS - 1), C::inv_lo(PASS)>(x, tile, pl, tid);
+            if (RED) reduce_top<C>(x, mod);
+        }
+        dit_pass<C, PASS>(x, tid, pyr, mod);
+        dit_all<C, RED, PASS + 1>(x, tile, pl, tid, pyr, mod);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// THE hot path: c = a * b in Z_q[x]/(x^N+1), one HBM round trip per polynomial
+// (new_reference/cg_ntt.py:78-92; rtl/ntt_poly_mult.sv:479-530 without its 20k copy cycles)
+//   NA = 1: forward(a), park it in registers, forward(b)       (one tile)
+//   NA = 2: forward(a) and forward(b) side by side, one twiddle load serves both (two tiles)
+// ---------------------------------------------------------------------------------------------
+template <class C, int NA, bool RED, int MINB>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
+               size_t batch, PolymulTables<typename C::W> tb, Mod<typename C::W> mod) {
+    using W = typename C::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tile = reinterpret_cast<W *>(smem_raw);
+    const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
+    const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
+    const bool active = poly < batch;
+    const size_t off = active ? poly * C::N : 0;
+
+    W fa[C::R];
+    if constexpr (NA == 1) {
+        W x[1][C::R];
+        row_load<C>(x[0], a + off, tid, active);
+        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) fa[k] = x[0][k];
+        row_load<C>(x[0], b + off, tid, active);
+        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) {
+            W u = fa[k], v = x[0][k];
+            if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
+            fa[k] = mont_mul(u, v, mod);
+        }
+    } else {
+        W x[2][C::R];
+        row_load<C>(x[0], a + off, tid, active);
+        row_load<C>(x[1], b + off, tid, active);
+        forward_all<C, 2, RED>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) {
+            W u = x[0][k], v = x[1][k];
+            if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
+            fa[k] = mont_mul(u, v, mod);
+        }
+    }
+    dit_all<C, RED>(fa, tile, pl, tid, tb.inv_pyr, mod);
+    row_store_scaled<C>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone natural-order transform (cg_ntt / cg_intt semantics, new_reference/cg_ntt.py:29-75):
+//   out = post * DFT_root(pre * in), all in natural order.  The bit-reversal of cg_ntt.py:39 /
+//   rtl/ntt_coeff_banks.v:112 happens on the way into the shared tile.
+// ---------------------------------------------------------------------------------------------
+template <class C, bool RED, int MINB>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
+                 TransformTables<typename C::W> tb, Mod<typename C::W> mod) {
+    using W = typename C::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tile = reinterpret_cast<W *>(smem_raw);
+    const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
+    const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
+    const bool active = poly < batch;
+    const size_t off = active ? poly * C::N : 0;
+
+    W x[C::R];
+    row_load<C>(x, in + off, tid, active);
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) {
+        const int e = (k << C::LOGP) + tid;
+        if (tb.pre) x[k] = shoup_mul(x[k], ld_tw(&tb.pre[e]), mod.q);
+        else if (tb.reduce_input) x[k] = shoup_mul(x[k], (W)1, mod.one_p, mod.q);
+        tile[C::spos(pl * C::N + bitrev_n(e, C::LOGN))] = x[k];
+    }
+    __syncthreads();
+    tile_read<C, 0>(x, tile, pl, tid);
+    dit_all<C, RED>(x, tile, pl, tid, tb.pyr, mod);
+    row_store_scaled<C>(x, out + off, tid, active, tb.post, tb.post_uniform, mod);
+}
+#endif  // __CUDACC__
+
+}  // namespace tntt

@@ -1,0 +1,19 @@
+// Fused negacyclic polymul kernels for uint64 coefficients, N = 4096: the north-star
+// configuration q = 2^60 - 2^14 + 1 of rtl/twiddle_forward_4096_60bit.hex (red = 1: lazy
+// top-bit reduction before every pass) and any smaller modulus (red = 0).
+#include "polymul_inst.cuh"
+
+namespace tntt {
+static const PolymulVariant kVariants[] = {
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 4, 1, 1, 1, 2),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 4, 1, 2, 1, 2),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 4, 1, 2, 1, 1),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 3, 1, 1, 1, 2),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 3, 1, 2, 1, 2),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 4, 1, 1, 0, 2),
+};
+const PolymulVariant *polymul_variants_u64(int *count) {
+    *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+    return kVariants;
+}
+}  // namespace tntt
