@@ -80,8 +80,9 @@ int tntt_plan_create_from_hex(tntt_plan **out, int device, uint32_t n, uint64_t 
                               const char *inv_hex_path);
 
 /* Writes the plan's psi^k (inverse = 0) or psi^-k table in the reference's hex format
- * (scripts/generate_twiddles.py:59-77): `hex_digits` upper-case digits per line. */
-int tntt_plan_write_hex(const tntt_plan *plan, const char *path, int inverse, int hex_digits);
+ * (scripts/generate_twiddles.py:59-77): `hex_digits` digits per line; the shipped N=256 and 60-bit
+ * tables are upper case, the 24-bit N=1024/4096 ones lower case. */
+int tntt_plan_write_hex(const tntt_plan *plan, const char *path, int inverse, int hex_digits, int uppercase);
 
 int tntt_plan_info_get(const tntt_plan *plan, tntt_plan_info *info);
 int tntt_plan_destroy(tntt_plan *plan);

@@ -24,14 +24,15 @@ def lib():
         L.emu_polymul.argtypes = [C.c_int] * 6 + [C.c_void_p] * 3 + [C.c_size_t, C.c_uint64, C.c_uint64]
         L.emu_transform.argtypes = [C.c_int] * 5 + [C.c_void_p] * 2 + [C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.emu_slot.argtypes = [C.c_int] * 7
-        for name, t in (("emu_shoup64", C.c_uint64), ("emu_mont64", C.c_uint64), ("emu_barrett64", C.c_uint64),
+        for name, t in (("emu_shoup64", C.c_uint64), ("emu_shoup_lazy64", C.c_uint64), ("emu_mont64", C.c_uint64), ("emu_barrett64", C.c_uint64),
                         ("emu_csub_top64", C.c_uint64), ("emu_shoup32", C.c_uint32), ("emu_mont32", C.c_uint32),
                         ("emu_barrett32", C.c_uint32)):
             getattr(L, name).restype = t
-        L.emu_shoup64.argtypes = L.emu_mont64.argtypes = L.emu_barrett64.argtypes = [C.c_uint64] * 3
+        L.emu_shoup64.argtypes = L.emu_shoup_lazy64.argtypes = L.emu_mont64.argtypes = L.emu_barrett64.argtypes = [C.c_uint64] * 3
         L.emu_shoup32.argtypes = L.emu_mont32.argtypes = L.emu_barrett32.argtypes = [C.c_uint32] * 3
         L.emu_csub_top64.argtypes = [C.c_uint64] * 2
         L.emu_is_prime.argtypes = [C.c_uint64]
+        L.emu_range_violations.restype = C.c_longlong
         L.emu_lazy_full_ok.argtypes = [C.c_int, C.c_uint64, C.c_int]
         _lib = L
     return _lib

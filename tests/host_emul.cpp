@@ -7,6 +7,7 @@
 // bit-for-bit against the oracle without a GPU.  It is not part of the product library and is
 // never used as a fallback; it also records the shared-memory slots touched per warp
 // instruction so tests/test_layout.py can count bank conflicts.
+#define TNTT_AUDIT_RANGES 1
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -15,10 +16,11 @@
 #include "../tiny-ntt_b200/csrc/tables.h"
 
 using namespace tntt;
+namespace tntt { long long g_range_violations = 0; }
 
 namespace {
 
-template <class C, int NA, bool RED> struct Emu {
+template <class C, int NA, bool RED, bool SOL = false> struct Emu {
     using W = typename C::W;
     static constexpr int T = C::THREADS;
     std::vector<W> tile;
@@ -40,26 +42,24 @@ template <class C, int NA, bool RED> struct Emu {
                         tile_write<C, C::fwd_lo(PASS - 1)>(X(t)[a], tl, t >> C::LOGP, t & (C::P - 1));
                     for (int t = 0; t < T; ++t) {
                         tile_read<C, C::fwd_lo(PASS)>(X(t)[a], tl, t >> C::LOGP, t & (C::P - 1));
-                        if (RED) reduce_top<C>(X(t)[a], mod);
                     }
                 }
             }
-            for (int t = 0; t < T; ++t) fwd_pass<C, PASS, NA>(X(t), t & (C::P - 1), tb, mod);
+            for (int t = 0; t < T; ++t) fwd_pass<C, PASS, NA, RED, SOL>(X(t), t & (C::P - 1), tb, mod);
             forward_from<PASS + 1>();
         }
     }
-    template <int PASS> void dit_from(const Tw<W> *pyr) {
+    template <int IN_BND, int PASS> void dit_from(const DitTables<W> &pyr) {
         if constexpr (PASS < C::NPASS) {
             if constexpr (PASS > 0) {
                 for (int t = 0; t < T; ++t)
                     tile_write<C, C::inv_lo(PASS - 1)>(F(t), tile.data(), t >> C::LOGP, t & (C::P - 1));
                 for (int t = 0; t < T; ++t) {
                     tile_read<C, C::inv_lo(PASS)>(F(t), tile.data(), t >> C::LOGP, t & (C::P - 1));
-                    if (RED) reduce_top<C>(F(t), mod);
                 }
             }
-            for (int t = 0; t < T; ++t) dit_pass<C, PASS>(F(t), t & (C::P - 1), pyr, mod);
-            dit_from<PASS + 1>(pyr);
+            for (int t = 0; t < T; ++t) dit_pass<C, PASS, RED, SOL, IN_BND>(F(t), t & (C::P - 1), pyr, mod);
+            dit_from<IN_BND, PASS + 1>(pyr);
         }
     }
 
@@ -83,9 +83,9 @@ template <class C, int NA, bool RED> struct Emu {
                 forward_from<0>();
                 for (int t = 0; t < T; ++t)
                     for (int k = 0; k < C::R; ++k) {
-                        W u = F(t)[k], v = X(t)[0][k];
-                        if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
-                        F(t)[k] = mont_mul(u, v, mod);
+                        W u = F(t)[k];
+                        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
+                        F(t)[k] = mont_mul(u, X(t)[0][k], mod);
                     }
             } else {
                 for (int t = 0; t < T; ++t) {
@@ -96,12 +96,12 @@ template <class C, int NA, bool RED> struct Emu {
                 forward_from<0>();
                 for (int t = 0; t < T; ++t)
                     for (int k = 0; k < C::R; ++k) {
-                        W u = X(t)[0][k], v = X(t)[NA - 1][k];
-                        if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
-                        F(t)[k] = mont_mul(u, v, mod);
+                        W u = X(t)[0][k];
+                        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
+                        F(t)[k] = mont_mul(u, X(t)[NA - 1][k], mod);
                     }
             }
-            dit_from<0>(tb.inv_pyr);
+            dit_from<pointwise_out_bound<C, RED>(), 0>(tb.inv);
             for (int t = 0; t < T; ++t) {
                 size_t o = off(t, act);
                 row_store_scaled<C>(F(t), c + o, t & (C::P - 1), act, tb.post, Tw<W>{0, 0}, mod);
@@ -123,13 +123,13 @@ template <class C, int NA, bool RED> struct Emu {
                 row_load<C>(F(t), in + o, tid, active);
                 for (int k = 0; k < C::R; ++k) {
                     const int e = (k << C::LOGP) + tid;
-                    if (tt.pre) F(t)[k] = shoup_mul(F(t)[k], ld_tw(&tt.pre[e]), mod.q);
-                    else if (tt.reduce_input) F(t)[k] = shoup_mul(F(t)[k], (W)1, mod.one_p, mod.q);
+                    if (tt.pre) F(t)[k] = shoup_mul(F(t)[k], ld_tw(&tt.pre[e]), mod.nq);
+                    else if (tt.reduce_input) F(t)[k] = shoup_mul(F(t)[k], (W)1, mod.one_p, mod.nq);
                     tile[C::spos(pl * C::N + bitrev_n(e, C::LOGN))] = F(t)[k];
                 }
             }
             for (int t = 0; t < T; ++t) tile_read<C, 0>(F(t), tile.data(), t >> C::LOGP, t & (C::P - 1));
-            dit_from<0>(tt.pyr);
+            dit_from<2, 0>(tt.dit);
             for (int t = 0; t < T; ++t) {
                 const size_t poly = cta * C::PPC + (t >> C::LOGP);
                 const bool active = poly < batch;
@@ -140,8 +140,9 @@ template <class C, int NA, bool RED> struct Emu {
     }
 };
 
-template <class C, int NA, bool RED>
+template <class C, int NA, bool RED, bool SOL = false>
 int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q, uint64_t psi) {
+    if (SOL && q != kSolinasQ) return -3;
     using W = typename C::W;
     constexpr int BITS = WordTraits<W>::BITS;
     if (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN)) return -2;
@@ -151,8 +152,12 @@ int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q,
     auto inv = host::dit_pyramid<W>(host::modinv(omega, q), C::N, q);
     const uint64_t scale = host::mulmod(host::modinv(C::N % q, q), (uint64_t)((((host::u128)1) << BITS) % q), q);
     auto post = host::scaled_powers<W>(host::modinv(psi, q), scale, C::N, q);
-    Emu<C, NA, RED> e;
-    e.tb = PolymulTables<W>{fwd.data(), last.data(), inv.data(), post.data()};
+    Emu<C, NA, RED, SOL> e;
+    e.tb.fwd_pyr = fwd.data();
+    e.tb.fwd_last = last.data();
+    e.tb.post = post.data();
+    e.tb.inv.pyr = inv.data();
+    for (int i = 0; i < MAX_R && i < C::N; ++i) { e.tb.fwd_head[i] = fwd[i]; e.tb.inv.head[i] = inv[i]; }
     e.mod = host::make_mod<W>(q);
     e.polymul((const W *)a, (const W *)b, (W *)c, batch);
     return 0;
@@ -170,7 +175,8 @@ int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t 
     if (twist && !inverse) pre = host::scaled_powers<W>(root, 1, C::N, q);
     if (twist && inverse) post = host::scaled_powers<W>(host::modinv(root, q), n_inv, C::N, q);
     TransformTables<W> tt;
-    tt.pyr = pyr.data();
+    tt.dit.pyr = pyr.data();
+    for (int i = 0; i < MAX_R && i < (int)pyr.size(); ++i) tt.dit.head[i] = pyr[i];
     tt.pre = pre.empty() ? nullptr : pre.data();
     tt.post = post.empty() ? nullptr : post.data();
     tt.post_uniform = host::make_tw<W>(inverse ? n_inv : 1, q);
@@ -185,7 +191,7 @@ int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t 
 
 #define POLY_CASE(WB, WT, LN, LR, PPC, NA_, RED_)                                                      \
     if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && na == NA_ && red == RED_)       \
-        return run_polymul<Cfg<WT, LN, LR, PPC>, NA_, (RED_ != 0)>(a, b, c, batch, q, psi);
+        return run_polymul<Cfg<WT, LN, LR, PPC>, NA_, ((RED_ & 1) != 0), ((RED_ & 2) != 0)>(a, b, c, batch, q, psi);
 #define XFORM_CASE(WB, WT, LN, LR, PPC, RED_)                                                          \
     if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && red == RED_)                    \
         return run_transform<Cfg<WT, LN, LR, PPC>, (RED_ != 0)>(in, out, batch, q, root, mode, reduce_input);
@@ -217,6 +223,10 @@ int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, co
     POLY_CASE(8, uint64_t, 12, 4, 1, 2, 1)
     POLY_CASE(8, uint64_t, 12, 3, 1, 1, 1)
     POLY_CASE(8, uint64_t, 12, 3, 1, 2, 1)
+    POLY_CASE(8, uint64_t, 12, 4, 1, 1, 3)   // red | solinas
+    POLY_CASE(8, uint64_t, 12, 4, 1, 2, 3)
+    POLY_CASE(8, uint64_t, 12, 3, 1, 2, 3)
+    POLY_CASE(8, uint64_t, 8, 4, 16, 1, 3)
     return -1;
 }
 
@@ -244,13 +254,15 @@ int emu_slot(int word_bytes, int logn, int logr, int lo, int pl, int tid, int k)
 }
 
 // arithmetic probes for tests/test_modarith.py
-uint64_t emu_shoup64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_mul(x, t.w, t.wp, q); }
-uint32_t emu_shoup32(uint32_t x, uint32_t w, uint32_t q) { auto t = host::make_tw<uint32_t>(w, q); return shoup_mul(x, t.w, t.wp, q); }
+uint64_t emu_shoup64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_mul(x, t.w, t.wp, (uint64_t)(0 - q)); }
+uint32_t emu_shoup32(uint32_t x, uint32_t w, uint32_t q) { auto t = host::make_tw<uint32_t>(w, q); return shoup_mul(x, t.w, t.wp, (uint32_t)(0u - q)); }
+uint64_t emu_shoup_lazy64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_lazy<false>(x, t.w, t.wp, host::make_mod<uint64_t>(q)); }
 uint64_t emu_mont64(uint64_t x, uint64_t y, uint64_t q) { return mont_mul(x, y, host::make_mod<uint64_t>(q)); }
 uint32_t emu_mont32(uint32_t x, uint32_t y, uint32_t q) { return mont_mul(x, y, host::make_mod<uint32_t>(q)); }
 uint64_t emu_barrett64(uint64_t x, uint64_t y, uint64_t q) { return barrett_mul(x, y, host::make_mod<uint64_t>(q)); }
 uint32_t emu_barrett32(uint32_t x, uint32_t y, uint32_t q) { return barrett_mul(x, y, host::make_mod<uint32_t>(q)); }
 uint64_t emu_csub_top64(uint64_t x, uint64_t q) { return csub_top(x, host::make_mod<uint64_t>(q).top_sub); }
+long long emu_range_violations(void) { return tntt::g_range_violations; }
 int emu_is_prime(uint64_t n) { return host::is_prime(n); }
 int emu_lazy_full_ok(int word_bytes, uint64_t q, int logn) {
     return word_bytes == 4 ? host::lazy_full_ok<uint32_t>(q, logn) : host::lazy_full_ok<uint64_t>(q, logn);

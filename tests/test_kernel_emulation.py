@@ -16,7 +16,9 @@ POLY = [(4, 8, 4, 16, 1, 0, "dilithium"), (4, 8, 4, 16, 2, 0, "dilithium"), (4, 
         (4, 12, 5, 2, 1, 0, "n4096_24"), (4, 12, 3, 1, 1, 0, "n4096_24"),
         (8, 12, 4, 1, 1, 1, "n4096_60"), (8, 12, 4, 1, 2, 1, "n4096_60"), (8, 12, 3, 1, 1, 1, "n4096_60"),
         (8, 12, 3, 1, 2, 1, "n4096_60"), (8, 12, 4, 1, 1, 0, "n4096_24"), (8, 8, 4, 16, 1, 0, "dilithium"),
-        (8, 8, 4, 16, 1, 1, "dilithium"), (8, 10, 4, 4, 1, 0, "n1024_24"), (8, 10, 4, 4, 1, 1, "n1024_24")]
+        (8, 8, 4, 16, 1, 1, "dilithium"), (8, 10, 4, 4, 1, 0, "n1024_24"), (8, 10, 4, 4, 1, 1, "n1024_24"),
+        # red | 2 = the Solinas (q = 2^60 - 2^14 + 1) specialisation
+        (8, 12, 4, 1, 1, 3, "n4096_60"), (8, 12, 4, 1, 2, 3, "n4096_60"), (8, 12, 3, 1, 2, 3, "n4096_60")]
 
 
 @pytest.fixture(scope="module")
@@ -38,6 +40,7 @@ def test_emulated_polymul_matches_oracle(wb, logn, logr, ppc, na, red, tag, co):
     want = co.nwc_poly_mult(a, b, psi, q, threads=4)
     got = emu.polymul(wb, logn, logr, ppc, na, red, a, b, q, psi).astype(np.uint64)
     assert (got == want).all()
+    assert emu.lib().emu_range_violations() == 0     # no lazy value ever wrapped around the word
 
 
 def test_emulated_tiny_sizes(co):
@@ -78,6 +81,7 @@ def test_emulated_transforms_match_oracle(wb, logn, logr, ppc, red, tag, co):
     assert tw[0].tolist() == O.forward_negacyclic([int(v) for v in x[0]], psi, q)   # ntt(twist(a))
     rt = emu.transform(wb, logn, logr, ppc, red, tw, q, psi, 3).astype(np.uint64)
     assert (rt == x[:1]).all()                                           # untwist(intt(...))
+    assert emu.lib().emu_range_violations() == 0
 
 
 def test_emulated_reduce_input_flag():
@@ -99,6 +103,8 @@ def test_modular_arithmetic_primitives():
         x, w = rnd.getrandbits(64), rnd.randrange(q60)
         t = L.emu_shoup64(x, w, q60)
         assert t < 2 * q60 and t % q60 == x * w % q60            # any 64-bit x -> [0, 2q)
+        t = L.emu_shoup_lazy64(x, w, q60)
+        assert t < 3 * q60 and t % q60 == x * w % q60            # butterfly product: [0, 3q)
         a, b = rnd.randrange(1 << 63), rnd.randrange(1 << 63)
         m = L.emu_mont64(a, b, q60)
         assert m < (1 << 62) + q60 and m * r64 % q60 == a * b % q60

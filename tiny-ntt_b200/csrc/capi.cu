@@ -83,6 +83,9 @@ struct tntt_plan {
     void *pre_twist = nullptr, *post_untwist = nullptr;                // psi^i ; psi^-i N^-1
     void *omega_pow = nullptr, *omega_inv_pow = nullptr;               // plain W[n]: literal CG stages
     Tw<uint64_t> one_tw{}, ninv_tw{};
+    // first MAX_R entries of the pyramids, passed by value in the kernel parameters
+    Tw<uint32_t> head32[3][MAX_R] = {};   // [0] fwd_pyr, [1] inv_pyr, [2] cyc_fwd_pyr
+    Tw<uint64_t> head64[3][MAX_R] = {};
     const TransformVariant *xform = nullptr;
     // host pipeline
     std::mutex pipe_mu;
@@ -101,9 +104,18 @@ template <typename W> int build_tables(tntt_plan *p) {
     const uint64_t q = p->info.q;
     const int logn = (int)p->info.logn;
     constexpr int BITS = WordTraits<W>::BITS;
+    auto keep_head = [&](const std::vector<Tw<W>> &v, int which) {
+        for (size_t i = 0; i < (size_t)MAX_R && i < v.size(); ++i) {
+            if constexpr (sizeof(W) == 4) p->head32[which][i] = v[i];
+            else p->head64[which][i] = v[i];
+        }
+    };
     if (p->info.omega_is_primitive) {
-        CUDA_TRY(upload(host::dit_pyramid<W>(p->info.omega, n, q), &p->cyc_fwd_pyr));
-        CUDA_TRY(upload(host::dit_pyramid<W>(p->info.omega_inv, n, q), &p->inv_pyr));
+        const std::vector<Tw<W>> cf = host::dit_pyramid<W>(p->info.omega, n, q), ci = host::dit_pyramid<W>(p->info.omega_inv, n, q);
+        CUDA_TRY(upload(cf, &p->cyc_fwd_pyr));
+        CUDA_TRY(upload(ci, &p->inv_pyr));
+        keep_head(cf, 2);
+        keep_head(ci, 1);
     }
     {   // natural power tables for the literal constant-geometry stages (any omega)
         std::vector<uint64_t> f = host::powers(p->info.omega, n, q), b = host::powers(p->info.omega_inv, n, q);
@@ -114,6 +126,7 @@ template <typename W> int build_tables(tntt_plan *p) {
     if (p->info.has_psi) {
         std::vector<Tw<W>> fwd = host::fwd_pyramid<W>(p->info.psi, n, q);
         CUDA_TRY(upload(fwd, &p->fwd_pyr));
+        keep_head(fwd, 0);
         for (const PolymulVariant &v : all_variants())
             if (v.word_bytes == (int)sizeof(W) && v.logn == logn && !p->fwd_last[v.logr])
                 CUDA_TRY(upload(host::fwd_last_table<W>(fwd, logn, v.logr), &p->fwd_last[v.logr]));
@@ -129,8 +142,8 @@ template <typename W> int build_tables(tntt_plan *p) {
 int choose_default_variant(const tntt_plan *p) {
     // preference order measured on B200 (profiles/): first match wins
     static const char *prefer[] = {
-        "u64_n12_r4_p1_a1_red1_b2", "u64_n12_r4_p1_a1_red0_b2", "u32_n12_r4_p1_a1_red0_b4",
-        "u32_n10_r4_p4_a1_red0_b4", "u32_n8_r4_p16_a1_red0_b4",
+        "u64_n12_r4_p1_a2_red1_b2_s0_sol1", "u64_n12_r4_p1_a2_red1_b2_s0_sol0", "u64_n12_r4_p1_a1_red0_b2_s0_sol0",
+        "u32_n12_r4_p1_a1_red0_b4_s0_sol0", "u32_n10_r5_p8_a1_red0_b2_s0_sol0", "u32_n8_r4_p16_a2_red0_b4_s0_sol0",
     };
     const std::vector<PolymulVariant> &vs = all_variants();
     for (const char *name : prefer)
@@ -216,8 +229,9 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
     return TNTT_OK;
 }
 
-int check_io(const tntt_plan *p, const void *a, const void *b) {
+int check_io(const tntt_plan *p, const void *a, const void *b, size_t batch = 1) {
     if (!p) return fail(TNTT_BAD_ARG, "plan is null");
+    if (batch == 0) return TNTT_OK;   // empty batches may come with null pointers
     if (!a || !b) return fail(TNTT_BAD_ARG, "null data pointer");
     if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(TNTT_BAD_ARG, "data pointers must be 16-byte aligned");
     return TNTT_OK;
@@ -250,7 +264,9 @@ int generic_transform(const tntt_plan *p, const void *in, void *out, size_t batc
 template <typename W>
 int fast_transform(const tntt_plan *p, const void *in, void *out, size_t batch, bool inverse, int flags, cudaStream_t st) {
     TransformTables<W> tt;
-    tt.pyr = (const Tw<W> *)(inverse ? p->inv_pyr : p->cyc_fwd_pyr);
+    tt.dit.pyr = (const Tw<W> *)(inverse ? p->inv_pyr : p->cyc_fwd_pyr);
+    if constexpr (sizeof(W) == 4) memcpy(tt.dit.head, p->head32[inverse ? 1 : 2], sizeof tt.dit.head);
+    else memcpy(tt.dit.head, p->head64[inverse ? 1 : 2], sizeof tt.dit.head);
     tt.pre = (!inverse && (flags & TNTT_TWIST)) ? (const Tw<W> *)p->pre_twist : nullptr;
     tt.post = (inverse && (flags & TNTT_TWIST)) ? (const Tw<W> *)p->post_untwist : nullptr;
     tt.post_uniform = host::make_tw<W>(inverse ? p->info.n_inv : 1, p->info.q);
@@ -260,7 +276,7 @@ int fast_transform(const tntt_plan *p, const void *in, void *out, size_t batch, 
 }
 
 int transform(const tntt_plan *p, const void *in, void *out, size_t batch, bool inverse, int flags, void *stream) {
-    int rc = check_io(p, in, out);
+    int rc = check_io(p, in, out, batch);
     if (rc) return rc;
     if (flags & ~(TNTT_TWIST | TNTT_REDUCE_INPUT)) return fail(TNTT_BAD_ARG, "unknown flag bits 0x%x", flags);
     if ((flags & TNTT_TWIST) && !p->info.has_psi) return fail(TNTT_BAD_ARG, "TNTT_TWIST needs a plan created from psi");
@@ -274,8 +290,13 @@ int transform(const tntt_plan *p, const void *in, void *out, size_t batch, bool 
 
 template <typename W> int launch_variant(const tntt_plan *p, const PolymulVariant &v, const void *a, const void *b, void *c,
                                          size_t batch, cudaStream_t st) {
-    PolymulTables<W> tb{(const Tw<W> *)p->fwd_pyr, (const Tw<W> *)p->fwd_last[v.logr], (const Tw<W> *)p->inv_pyr,
-                        (const Tw<W> *)p->post_mont};
+    PolymulTables<W> tb;
+    tb.fwd_pyr = (const Tw<W> *)p->fwd_pyr;
+    tb.fwd_last = (const Tw<W> *)p->fwd_last[v.logr];
+    tb.post = (const Tw<W> *)p->post_mont;
+    tb.inv.pyr = (const Tw<W> *)p->inv_pyr;
+    if constexpr (sizeof(W) == 4) { memcpy(tb.fwd_head, p->head32[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head32[1], sizeof tb.inv.head); }
+    else { memcpy(tb.fwd_head, p->head64[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head64[1], sizeof tb.inv.head); }
     CUDA_TRY(v.launch(a, b, c, batch, &tb, p->mod(), st));
     return TNTT_OK;
 }
@@ -344,13 +365,13 @@ int tntt_plan_create_from_hex(tntt_plan **out, int device, uint32_t n, uint64_t 
     return create_plan(out, device, n, q, psi, 1);
 }
 
-int tntt_plan_write_hex(const tntt_plan *plan, const char *path, int inverse, int hex_digits) {
+int tntt_plan_write_hex(const tntt_plan *plan, const char *path, int inverse, int hex_digits, int uppercase) {
     if (!plan || !path) return fail(TNTT_BAD_ARG, "null argument");
     if (!plan->info.has_psi) return fail(TNTT_BAD_ARG, "plan has no psi");
     if (hex_digits < 1 || hex_digits > 16) return fail(TNTT_BAD_ARG, "hex_digits out of range");
     FILE *f = fopen(path, "w");
     if (!f) return fail(TNTT_IO_ERROR, "cannot open %s for writing", path);
-    for (uint64_t v : (inverse ? plan->psi_inv_pow : plan->psi_pow)) fprintf(f, "%0*llX\n", hex_digits, (unsigned long long)v);
+    for (uint64_t v : (inverse ? plan->psi_inv_pow : plan->psi_pow)) fprintf(f, uppercase ? "%0*llX\n" : "%0*llx\n", hex_digits, (unsigned long long)v);
     fclose(f);
     return TNTT_OK;
 }
@@ -383,8 +404,9 @@ int tntt_inverse(const tntt_plan *plan, const void *in, void *out, size_t batch,
 }
 
 int tntt_pointwise(const tntt_plan *p, const void *a, const void *b, void *c, size_t batch, void *stream) {
-    int rc = check_io(p, a, b);
+    int rc = check_io(p, a, b, batch);
     if (rc) return rc;
+    if (batch == 0) return TNTT_OK;
     if (!c) return fail(TNTT_BAD_ARG, "null data pointer");
     DeviceSetter ds(p->info.device);
     CUDA_TRY(launch_pointwise(p->info.word_bytes, a, b, c, batch * p->info.n, p->mod(), (cudaStream_t)stream));
@@ -399,8 +421,8 @@ int tntt_variant_describe(int variant, char *buf, size_t buflen) {
     int occ = 0;
     const bool have = v.attributes(&attr, &occ) == cudaSuccess;
     if (!have) cudaGetLastError();
-    snprintf(buf, buflen, "%s word=%d n=%d r=%d ppc=%d na=%d red=%d threads=%d smem=%zu regs=%d local=%zu ctas_per_sm=%d",
-             v.name, v.word_bytes, 1 << v.logn, 1 << v.logr, v.ppc, v.na, v.red, v.threads, v.smem,
+    snprintf(buf, buflen, "%s word=%d n=%d r=%d ppc=%d na=%d red=%d sol=%d threads=%d smem=%zu regs=%d local=%zu ctas_per_sm=%d",
+             v.name, v.word_bytes, 1 << v.logn, 1 << v.logr, v.ppc, v.na, v.red, v.sol, v.threads, v.smem,
              have ? attr.numRegs : -1, have ? attr.localSizeBytes : (size_t)0, have ? occ : -1);
     return TNTT_OK;
 }
@@ -409,6 +431,7 @@ int tntt_variant_matches(const tntt_plan *p, int variant) {
     const PolymulVariant &v = all_variants()[variant];
     if (!p->info.has_psi || v.word_bytes != p->info.word_bytes || v.logn != (int)p->info.logn) return 0;
     if (v.red != p->info.lazy_reduce) return 0;
+    if (v.sol && p->info.q != kSolinasQ) return 0;
     if (v.red && !host::lazy_pass_ok<uint64_t>(p->info.q, v.logr)) return 0;
     return 1;
 }
@@ -419,8 +442,9 @@ int tntt_plan_set_default_variant(tntt_plan *p, int variant) {
 }
 
 int tntt_polymul_variant(const tntt_plan *p, int variant, const void *a, const void *b, void *c, size_t batch, void *stream) {
-    int rc = check_io(p, a, b);
+    int rc = check_io(p, a, b, batch);
     if (rc) return rc;
+    if (batch == 0) return TNTT_OK;
     if (!c || ((uintptr_t)c & 15)) return fail(TNTT_BAD_ARG, "c must be a 16-byte aligned device pointer");
     if (!tntt_variant_matches(p, variant)) return fail(TNTT_BAD_ARG, "variant %d does not match the plan", variant);
     DeviceSetter ds(p->info.device);
@@ -430,11 +454,11 @@ int tntt_polymul_variant(const tntt_plan *p, int variant, const void *a, const v
 }
 
 int tntt_polymul(const tntt_plan *p, const void *a, const void *b, void *c, size_t batch, void *stream) {
-    int rc = check_io(p, a, b);
+    int rc = check_io(p, a, b, batch);
     if (rc) return rc;
-    if (!c || ((uintptr_t)c & 15)) return fail(TNTT_BAD_ARG, "c must be a 16-byte aligned device pointer");
     if (!p->info.has_psi) return fail(TNTT_BAD_ARG, "polymul needs a plan created from psi");
     if (batch == 0) return TNTT_OK;
+    if (!c || ((uintptr_t)c & 15)) return fail(TNTT_BAD_ARG, "c must be a 16-byte aligned device pointer");
     if (p->info.default_variant >= 0) return tntt_polymul_variant(p, p->info.default_variant, a, b, c, batch, stream);
     DeviceSetter ds(p->info.device);
     return generic_polymul(p, a, b, c, batch, (cudaStream_t)stream);

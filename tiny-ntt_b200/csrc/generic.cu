@@ -60,7 +60,7 @@ mul_table_kernel(const W *__restrict__ in, W *__restrict__ out, size_t batch, in
     const size_t n = (size_t)1 << logn, total = batch * n;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const Tw<W> t = ld_tw(&table[idx & (n - 1)]);
-        out[idx] = csub(shoup_mul(in[idx], t.w, t.wp, mod.q), mod.q);
+        out[idx] = csub(shoup_mul(in[idx], t.w, t.wp, mod.nq), mod.q);
     }
 }
 
@@ -68,7 +68,7 @@ template <typename W>
 __global__ void __launch_bounds__(kThreads)
 scale_kernel(const W *__restrict__ in, W *__restrict__ out, size_t count, W w, W wp, Mod<W> mod) {
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x)
-        out[idx] = csub(shoup_mul(in[idx], w, wp, mod.q), mod.q);
+        out[idx] = csub(shoup_mul(in[idx], w, wp, mod.nq), mod.q);
 }
 
 // 8-lane (or any-lane) butterfly batch of new_reference/cg_ntt_8butterfly.py:8-27 / rtl/ntt_butterfly.v:43-72

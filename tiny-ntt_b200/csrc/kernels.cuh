@@ -27,11 +27,6 @@
 
 namespace tntt {
 
-#if defined(__CUDACC__)
-#define TNTT_CX __host__ __device__ constexpr
-#else
-#define TNTT_CX constexpr
-#endif
 TNTT_CX int cmax(int a, int b) { return a > b ? a : b; }
 TNTT_CX int cmin(int a, int b) { return a < b ? a : b; }
 
@@ -63,15 +58,25 @@ template <typename W_, int LOGN_, int LOGR_, int PPC_> struct Cfg {
     static constexpr int FWD_LAST_ENTRIES = (R - 1) * P;
 };
 
-// Device view of the tables of one plan for one kernel variant.
+// Device view of the tables of one plan for one kernel variant.  The first MAX_R entries of each
+// pyramid are also carried BY VALUE in the kernel parameters: the first forward pass and the first
+// inverse pass use the same twiddles in every thread, and with compile-time indices into the
+// parameter block they become constant-bank operands of the IMADs (no load, no register) -- the
+// per-CTA "twiddle cache" of rtl/twiddle_bram_multiport.v for the uniform stages.
+constexpr int MAX_R = 32;
+template <typename W> struct DitTables {
+    const Tw<W> *pyr;       // [N] DIT pyramid of a root: entry t+j = root^(j*N/(2t)), t = 2^b, j < t
+    Tw<W> head[MAX_R];      // pyr[0 .. MAX_R)
+};
 template <typename W> struct PolymulTables {
     const Tw<W> *fwd_pyr;   // [N]  psi^bitrev pyramid: entry m+i, m = 2^stage
     const Tw<W> *fwd_last;  // [(R-1)*P] the same values for the last forward pass, [slot][tid]
-    const Tw<W> *inv_pyr;   // [N]  omega^-1 DIT pyramid: entry t+j = omega^(-j*N/(2t))
     const Tw<W> *post;      // [N]  psi^-i * N^-1 * 2^BITS (the 2^BITS undoes the Montgomery pointwise product)
+    Tw<W> fwd_head[MAX_R];  // fwd_pyr[0 .. MAX_R)
+    DitTables<W> inv;       // omega^-1
 };
 template <typename W> struct TransformTables {
-    const Tw<W> *pyr;   // [N] DIT pyramid of the root (omega or omega^-1)
+    DitTables<W> dit;   // pyramid of the root (omega or omega^-1)
     const Tw<W> *pre;   // [N] multiply on load (psi^i) or nullptr
     const Tw<W> *post;  // [N] multiply on store (psi^-i N^-1) or nullptr -> post_uniform
     Tw<W> post_uniform; // {1, floor(2^BITS/q)} (forward) or {N^-1, ...} (inverse)
@@ -93,9 +98,20 @@ template <typename W> TNTT_HD Tw<W> ld_tw(const Tw<W> *p) {
 }
 template <typename W> TNTT_HD W ld_stream(const W *p) {
 #if defined(__CUDA_ARCH__)
-    return __ldcs(p);  // coefficients are touched once: evict-first, keeps the twiddles cached
+    W v;  // coefficients are touched once: do not let them displace the twiddle tables from L1
+    if constexpr (sizeof(W) == 4) asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
 #else
     return *p;
+#endif
+}
+// pull a twiddle line towards L1 without holding a register for it (no-op on the host)
+TNTT_HD void prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
 #endif
 }
 template <typename W> TNTT_HD void st_stream(W *p, W v) {
@@ -106,12 +122,21 @@ template <typename W> TNTT_HD void st_stream(W *p, W v) {
 #endif
 }
 
+// Lazy reduction before a stage: only the registers that enter it as the un-multiplied ("x") input
+// need it -- the other input goes through shoup_mul(), which accepts
+// any word, and every later stage inherits bound(x) + 2q.  KB = register-index bit of that stage.
+template <class C, int KB> TNTT_HD void reduce_top_x(typename C::W (&x)[C::R], const Mod<typename C::W> &mod) {
+#pragma unroll
+    for (int k = 0; k < C::R; ++k)
+        if (!(k & (1 << KB))) x[k] = csub_top(x[k], mod.top_sub);
+}
+
 // ---------------------------------------------------------------------------------------------
 // merged-psi Cooley-Tukey pass (natural -> bit-reversed), NA operands sharing each twiddle
 // ---------------------------------------------------------------------------------------------
 // one stage (index bit B) of a forward pass; B is a template parameter so that every loop bound
 // below is a compile-time constant and the register arrays never fall into local memory
-template <class C, int PASS, int NA, int B>
+template <class C, int PASS, int NA, bool RED, bool SOL, int B>
 TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                        const Mod<typename C::W> &mod) {
     using W = typename C::W;
@@ -119,56 +144,94 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
     constexpr int kb = B - LO;            // bit of the register index this stage pairs over
     constexpr int s = C::LOGN - 1 - B;    // stage number: 2^s blocks
     constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
+    if constexpr (stage_needs_reduction(RED, Growth<W>::G, bound_at(RED, Growth<W>::G, 1, s))) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) reduce_top_x<C, kb>(x[a], mod);
+    }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         Tw<W> t;
-        if constexpr (LO == 0)  // last pass: every thread has its own twiddles -> transposed table, coalesced
+        if constexpr (LO == C::LOGP && C::R <= MAX_R)  // first pass: same twiddle in every thread -> kernel parameter
+            t = tb.fwd_head[(1 << s) + g];
+        else if constexpr (LO == 0)  // last pass: every thread has its own twiddles -> transposed table, coalesced
             t = ld_tw(&tb.fwd_last[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
-        else                    // earlier passes: uniform or shared by 2^LO consecutive threads -> broadcast
+        else                    // middle passes: shared by 2^LO consecutive threads -> broadcast
             t = ld_tw(&tb.fwd_pyr[(1 << s) + ((tid >> LO) << (C::LOGR - 1 - kb)) + g]);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
 #pragma unroll
-            for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], t, mod);
+            for (int a = 0; a < NA; ++a) ct_butterfly<SOL>(x[a][k0], x[a][k1], t, mod);
         }
     }
-    if constexpr (B > LO) fwd_stage<C, PASS, NA, B - 1>(x, tid, tb, mod);
+    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, SOL, B - 1>(x, tid, tb, mod);
 }
-template <class C, int PASS, int NA>
+// The last forward pass, the last inverse pass and the final scaling read per-thread-distinct
+// table entries (about N*16 B each, together more than L1 holds next to the tiles).  They are
+// prefetched one pass ahead so that the L2 latency is paid while butterflies are running.
+template <class C> TNTT_HD void prefetch_fwd_last(int tid, const PolymulTables<typename C::W> &tb) {
+    constexpr int LAST = C::NPASS - 1;
+    constexpr int first_slot = (1 << (C::LOGR - (C::fwd_bhi(LAST) - C::fwd_lo(LAST)))) - 1;
+#pragma unroll
+    for (int slot = first_slot; slot < C::R - 1; ++slot) prefetch_l1(&tb.fwd_last[slot * C::P + tid]);
+}
+template <class C> TNTT_HD void prefetch_dit_last(int tid, const Tw<typename C::W> *pyr) {
+    constexpr int LAST = C::NPASS - 1, LO = C::inv_lo(LAST);
+    if (LO == 0) return;
+#pragma unroll
+    for (int b = C::inv_blo(LAST); b < C::inv_bhi(LAST); ++b)
+#pragma unroll
+        for (int j = 0; j < (1 << (b - LO)); ++j) prefetch_l1(&pyr[(1 << b) + (j << LO) + (tid & ((1 << LO) - 1))]);
+}
+template <class C> TNTT_HD void prefetch_post(int tid, const Tw<typename C::W> *post) {
+    if (!post) return;
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) prefetch_l1(&post[(k << C::LOGP) + tid]);
+}
+
+template <class C, int PASS, int NA, bool RED, bool SOL>
 TNTT_HD void fwd_pass(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                       const Mod<typename C::W> &mod) {
-    fwd_stage<C, PASS, NA, C::fwd_bhi(PASS) - 1>(x, tid, tb, mod);
+    fwd_stage<C, PASS, NA, RED, SOL, C::fwd_bhi(PASS) - 1>(x, tid, tb, mod);
+}
+// bound (units of 2^(BITS-4)) of the spectrum a forward transform of canonical input leaves in registers
+template <class C, bool RED> TNTT_CX int fwd_out_bound() {
+    return bound_at(RED, Growth<typename C::W>::G, 1, C::LOGN);
+}
+// ... and of the Montgomery product of a top-reduced u with such a v:  u*v/2^BITS + q
+template <class C, bool RED> TNTT_CX int pointwise_out_bound() {
+    constexpr int bf = fwd_out_bound<C, RED>();
+    return ((bf > 8 ? 8 : bf) * bf + 15) / 16 + 1;
 }
 
 // ---------------------------------------------------------------------------------------------
 // cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
 // ---------------------------------------------------------------------------------------------
-template <class C, int PASS, int B>
-TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const Tw<typename C::W> *pyr, const Mod<typename C::W> &mod) {
+// IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
+template <class C, int PASS, bool RED, bool SOL, int IN_BND, int B>
+TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
     using W = typename C::W;
     constexpr int LO = C::inv_lo(PASS);
     constexpr int kb = B - LO;
     constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
+    if constexpr (stage_needs_reduction(RED, Growth<W>::G, bound_at(RED, Growth<W>::G, IN_BND, B)))
+        reduce_top_x<C, kb>(x, mod);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        const Tw<W> t = ld_tw(&pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
+        Tw<W> t;
+        if constexpr (LO == 0 && C::R <= MAX_R) t = dt.head[(1 << B) + j];  // first pass: uniform -> kernel parameter
+        else t = ld_tw(&dt.pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
-            ct_butterfly(x[k0], x[k1], t, mod);
+            ct_butterfly<SOL>(x[k0], x[k1], t, mod);
         }
     }
-    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, B + 1>(x, tid, pyr, mod);
+    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, SOL, IN_BND, B + 1>(x, tid, dt, mod);
 }
-template <class C, int PASS>
-TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const Tw<typename C::W> *pyr, const Mod<typename C::W> &mod) {
-    dit_stage<C, PASS, C::inv_blo(PASS)>(x, tid, pyr, mod);
-}
-
-template <class C> TNTT_HD void reduce_top(typename C::W (&x)[C::R], const Mod<typename C::W> &mod) {
-#pragma unroll
-    for (int k = 0; k < C::R; ++k) x[k] = csub_top(x[k], mod.top_sub);
+template <class C, int PASS, bool RED, bool SOL, int IN_BND>
+TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
+    dit_stage<C, PASS, RED, SOL, IN_BND, C::inv_blo(PASS)>(x, tid, dt, mod);
 }
 
 // registers -> swizzled tile (layout with the register field at LO)
@@ -207,7 +270,7 @@ TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row
     for (int k = 0; k < C::R; ++k) {
         const int e = (k << C::LOGP) + tid;
         const Tw<W> t = post ? ld_tw(&post[e]) : post_uniform;
-        const W v = csub(shoup_mul(x[k], t.w, t.wp, mod.q), mod.q);
+        const W v = csub(shoup_mul(x[k], t.w, t.wp, mod.nq), mod.q);
         if (active) st_stream(row + e, v);
     }
 }
@@ -224,7 +287,7 @@ __device__ __forceinline__ void exchange(typename C::W (&x)[C::R], typename C::W
     tile_read<C, LO_TO>(x, tile, pl, tid);
 }
 
-template <class C, int NA, bool RED, int PASS = 0>
+template <class C, int NA, bool RED, bool SOL, int PASS = 0>
 __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typename C::W *tile, int pl, int tid,
                                             const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod) {
     if constexpr (PASS < C::NPASS) {
@@ -232,24 +295,26 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
                 exchange<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[a], tile + a * C::PPC * C::N, pl, tid);
-                if (RED) reduce_top<C>(x[a], mod);
             }
         }
-        fwd_pass<C, PASS, NA>(x, tid, tb, mod);
-        forward_all<C, NA, RED, PASS + 1>(x, tile, pl, tid, tb, mod);
+        if constexpr (PASS + 2 == C::NPASS) prefetch_fwd_last<C>(tid, tb);
+        fwd_pass<C, PASS, NA, RED, SOL>(x, tid, tb, mod);
+        forward_all<C, NA, RED, SOL, PASS + 1>(x, tile, pl, tid, tb, mod);
     }
 }
 
-template <class C, bool RED, int PASS = 0>
+template <class C, bool RED, bool SOL, int IN_BND, int PASS = 0>
 __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid,
-                                        const Tw<typename C::W> *pyr, const Mod<typename C::W> &mod) {
+                                        const DitTables<typename C::W> &dt, const Tw<typename C::W> *post,
+                                        const Mod<typename C::W> &mod) {
     if constexpr (PASS < C::NPASS) {
         if constexpr (PASS > 0) {
             exchange<C, C::inv_lo(PASS - 1), C::inv_lo(PASS)>(x, tile, pl, tid);
-            if (RED) reduce_top<C>(x, mod);
         }
-        dit_pass<C, PASS>(x, tid, pyr, mod);
-        dit_all<C, RED, PASS + 1>(x, tile, pl, tid, pyr, mod);
+        if constexpr (PASS + 2 == C::NPASS) prefetch_dit_last<C>(tid, dt.pyr);
+        if constexpr (PASS + 1 == C::NPASS) prefetch_post<C>(tid, post);
+        dit_pass<C, PASS, RED, SOL, IN_BND>(x, tid, dt, mod);
+        dit_all<C, RED, SOL, IN_BND, PASS + 1>(x, tile, pl, tid, dt, post, mod);
     }
 }
 
@@ -259,10 +324,13 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
 //   NA = 1: forward(a), park it in registers, forward(b)       (one tile)
 //   NA = 2: forward(a) and forward(b) side by side, one twiddle load serves both (two tiles)
 // ---------------------------------------------------------------------------------------------
-template <class C, int NA, bool RED, int MINB>
+//   STASH = 1 (NA = 1 only): a's spectrum waits in a second shared tile instead of in registers while
+//              b is transformed (thread-private slots, [k][thread] order: no conflicts, no barrier)
+template <class C, int NA, bool RED, int MINB, int STASH = 0, bool SOL = false>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
-               size_t batch, PolymulTables<typename C::W> tb, Mod<typename C::W> mod) {
+               size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
+               const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W *tile = reinterpret_cast<W *>(smem_raw);
@@ -274,31 +342,37 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     W fa[C::R];
     if constexpr (NA == 1) {
         W x[1][C::R];
+        W *stash = tile + C::PPC * C::N + threadIdx.x;
         row_load<C>(x[0], a + off, tid, active);
-        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
-#pragma unroll
-        for (int k = 0; k < C::R; ++k) fa[k] = x[0][k];
-        row_load<C>(x[0], b + off, tid, active);
-        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 1, RED, SOL>(x, tile, pl, tid, tb, mod);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
-            W u = fa[k], v = x[0][k];
-            if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
-            fa[k] = mont_mul(u, v, mod);
+            if constexpr (STASH) stash[k * C::THREADS] = x[0][k];
+            else fa[k] = x[0][k];
+        }
+        row_load<C>(x[0], b + off, tid, active);
+        forward_all<C, 1, RED, SOL>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) {
+            W u;
+            if constexpr (STASH) u = stash[k * C::THREADS];
+            else u = fa[k];
+            if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);  // u < 2^(BITS-1): no overflow
+            fa[k] = mont_mul(u, x[0][k], mod);
         }
     } else {
         W x[2][C::R];
         row_load<C>(x[0], a + off, tid, active);
         row_load<C>(x[1], b + off, tid, active);
-        forward_all<C, 2, RED>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 2, RED, SOL>(x, tile, pl, tid, tb, mod);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
-            W u = x[0][k], v = x[1][k];
-            if (RED) { u = csub_top(u, mod.top_sub); v = csub_top(v, mod.top_sub); }
-            fa[k] = mont_mul(u, v, mod);
+            W u = x[0][k];
+            if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
+            fa[k] = mont_mul(u, x[1][k], mod);
         }
     }
-    dit_all<C, RED>(fa, tile, pl, tid, tb.inv_pyr, mod);
+    dit_all<C, RED, SOL, pointwise_out_bound<C, RED>()>(fa, tile, pl, tid, tb.inv, tb.post, mod);
     row_store_scaled<C>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
 }
 
@@ -310,7 +384,8 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
 template <class C, bool RED, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
-                 TransformTables<typename C::W> tb, Mod<typename C::W> mod) {
+                 const __grid_constant__ TransformTables<typename C::W> tb,
+                 const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W *tile = reinterpret_cast<W *>(smem_raw);
@@ -324,13 +399,13 @@ transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict
 #pragma unroll
     for (int k = 0; k < C::R; ++k) {
         const int e = (k << C::LOGP) + tid;
-        if (tb.pre) x[k] = shoup_mul(x[k], ld_tw(&tb.pre[e]), mod.q);
-        else if (tb.reduce_input) x[k] = shoup_mul(x[k], (W)1, mod.one_p, mod.q);
+        if (tb.pre) x[k] = shoup_mul(x[k], ld_tw(&tb.pre[e]), mod.nq);
+        else if (tb.reduce_input) x[k] = shoup_mul(x[k], (W)1, mod.one_p, mod.nq);
         tile[C::spos(pl * C::N + bitrev_n(e, C::LOGN))] = x[k];
     }
     __syncthreads();
     tile_read<C, 0>(x, tile, pl, tid);
-    dit_all<C, RED>(x, tile, pl, tid, tb.pyr, mod);
+    dit_all<C, RED, false, 2>(x, tile, pl, tid, tb.dit, tb.post, mod);
     row_store_scaled<C>(x, out + off, tid, active, tb.post, tb.post_uniform, mod);
 }
 #endif  // __CUDACC__

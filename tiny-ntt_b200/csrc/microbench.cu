@@ -32,7 +32,7 @@ template <typename W> __global__ void __launch_bounds__(256) modmul_kernel(W *si
     for (int i = 0; i < kIlp; ++i) x[i] = seed + threadIdx.x * 977u + i;
     for (int it = 0; it < kIters; ++it) {
 #pragma unroll
-        for (int i = 0; i < kIlp; ++i) x[i] = shoup_mul(x[i], t.w, t.wp, mod.q);
+        for (int i = 0; i < kIlp; ++i) x[i] = shoup_mul(x[i], t.w, t.wp, mod.nq);
     }
     W r = 0;
 #pragma unroll
@@ -51,8 +51,8 @@ cudaError_t run_microbench(int kind, double *ops_per_second) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    Mod<uint64_t> m64{}; m64.q = 1152921504606830593ull;
-    Mod<uint32_t> m32{}; m32.q = 8380417u;
+    Mod<uint64_t> m64{}; m64.q = 1152921504606830593ull; m64.nq = 0 - m64.q;
+    Mod<uint32_t> m32{}; m32.q = 8380417u; m32.nq = 0u - m32.q;
     Tw<uint64_t> t64{431606828070683274ull, 6905709249130932383ull};
     Tw<uint32_t> t32{1239911u, 635448320u};
     float best = 1e30f;

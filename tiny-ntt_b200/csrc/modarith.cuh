@@ -18,8 +18,10 @@
 
 #if defined(__CUDACC__)
 #define TNTT_HD __host__ __device__ __forceinline__
+#define TNTT_CX __host__ __device__ constexpr
 #else
 #define TNTT_HD inline
+#define TNTT_CX constexpr
 #endif
 
 namespace tntt {
@@ -50,7 +52,9 @@ template <typename W> struct alignas(2 * sizeof(W)) Tw { W w, wp; };
 // ---------------------------------------------------------------- modulus constants
 template <typename W> struct Mod {
     W q;        // modulus
+    W nq;       // 2^BITS - q  (so that x*w - h*q == x*w + h*nq without a negation)
     W q2;       // 2q
+    W qg;       // GROWTH*q: what a butterfly adds to keep x - w*y non-negative (2q for 32-bit, 3q for 64-bit words)
     W top_sub;  // floor(2^(BITS-1)/q)*q : what csub_top() subtracts
     W nqinv;    // -q^-1 mod 2^BITS  (Montgomery)
     W one_p;    // floor(2^BITS / q) : Shoup companion of 1
@@ -58,12 +62,47 @@ template <typename W> struct Mod {
     int k;      // Barrett k
 };
 
-// x*w mod q in [0, 2q) for ANY word x; w < q, wp = floor(w*2^BITS/q).   3 / 10 IMAD32
-template <typename W> TNTT_HD W shoup_mul(W x, W w, W wp, W q) {
-    const W h = mulhi(x, wp);
-    return x * w - h * q;
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void unpack64(uint64_t v, uint32_t &lo, uint32_t &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
 }
-template <typename W> TNTT_HD W shoup_mul(W x, const Tw<W> &t, W q) { return shoup_mul(x, t.w, t.wp, q); }
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
+}
+#endif
+
+// x*w mod q in [0, 2q) for ANY word x; w < q, wp = floor(w*2^BITS/q), nq = 2^BITS - q.
+// 32-bit: 3 IMAD.  64-bit: 10 IMAD + 3 carry ops = 13 SASS instructions -- the low 64 bits of
+// x*w + h*nq are accumulated through one IMAD.WIDE chain and four IMAD.LO into the high word
+// (pinned with PTX: left to itself nvcc builds both 64-bit products separately and negates).
+TNTT_HD uint32_t shoup_mul(uint32_t x, uint32_t w, uint32_t wp, uint32_t nq) {
+    const uint32_t h = mulhi(x, wp);
+    return x * w + h * nq;
+}
+TNTT_HD uint64_t shoup_mul(uint64_t x, uint64_t w, uint64_t wp, uint64_t nq) {
+    const uint64_t h = mulhi(x, wp);
+#if defined(__CUDA_ARCH__)
+    uint32_t x0, x1, w0, w1, h0, h1, n0, n1, lo, hi;
+    unpack64(x, x0, x1);
+    unpack64(w, w0, w1);
+    unpack64(h, h0, h1);
+    unpack64(nq, n0, n1);
+    uint64_t acc;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(x0), "r"(w0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
+    unpack64(acc, lo, hi);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(x0), "r"(w1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(x1), "r"(w0));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h0), "r"(n1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(n0));
+    return pack64(lo, hi);
+#else
+    return x * w + h * nq;
+#endif
+}
+template <typename W> TNTT_HD W shoup_mul(W x, const Tw<W> &t, W nq) { return shoup_mul(x, t.w, t.wp, nq); }
 
 // [0, 2q) -> [0, q)
 template <typename W> TNTT_HD W csub(W x, W q) { return x >= q ? x - q : x; }
@@ -71,19 +110,120 @@ template <typename W> TNTT_HD W csub(W x, W q) { return x >= q ? x - q : x; }
 // any word -> value < max(2^(BITS-1), x - top_sub): keeps lazy values from overflowing.
 // Tests only the top bit (one ISETP on the high half for 64-bit words).
 TNTT_HD uint32_t csub_top(uint32_t x, uint32_t top_sub) { return ((int32_t)x < 0) ? x - top_sub : x; }
-TNTT_HD uint64_t csub_top(uint64_t x, uint64_t top_sub) { return ((int64_t)x < 0) ? x - top_sub : x; }
+TNTT_HD uint64_t csub_top(uint64_t x, uint64_t top_sub) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo, hi, c0, c1;
+    unpack64(x, lo, hi);
+    unpack64(top_sub, c0, c1);
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\t@p sub.cc.u32 %0, %0, %2;\n\t@p subc.u32 %1, %1, %3;\n\t}"
+        : "+r"(lo), "+r"(hi) : "r"(c0), "r"(c1));
+    return pack64(lo, hi);
+#else
+    return ((int64_t)x < 0) ? x - top_sub : x;
+#endif
+}
 
-// Cooley-Tukey butterfly on lazy values: (x, y) <- (x + w*y, x - w*y + 2q).  Grows the bound by 2q.
-template <typename W> TNTT_HD void ct_butterfly(W &x, W &y, const Tw<W> &t, const Mod<W> &m) {
-    const W v = shoup_mul(y, t.w, t.wp, m.q);
-    y = x - v + m.q2;
+// Host-only audit used by tests/host_emul.cpp: counts lazy values that wrapped around 2^BITS.
+#if !defined(__CUDA_ARCH__) && defined(TNTT_AUDIT_RANGES)
+extern long long g_range_violations;
+template <typename W> inline void audit_butterfly(W x, W v, W qg) {
+    const unsigned __int128 lim = (unsigned __int128)1 << WordTraits<W>::BITS;
+    if ((unsigned __int128)x + v >= lim || (unsigned __int128)x + qg >= lim + v || v >= qg) ++g_range_violations;
+}
+#define TNTT_AUDIT_BUTTERFLY(x, v, qg) audit_butterfly(x, v, qg)
+#else
+#define TNTT_AUDIT_BUTTERFLY(x, v, qg)
+#endif
+
+// ---------------------------------------------------------------- the butterfly product
+// w*y mod q for the butterflies, result in [0, GROWTH*q) for ANY word y.
+//  32-bit words: exact Shoup, GROWTH = 2  (IMAD.HI + 2 IMAD).
+//  64-bit words: GROWTH = 3.  On sm_100a IMAD.WIDE / IMAD.HI issue at half the IMAD.LO rate
+//    (measured, tools/ubench), so the 64x64 high product is the expensive part.  The lowest partial
+//    product y0*p0 is dropped: h' = floor((y1*p1*2^64 + (y0*p1 + y1*p0)*2^32) / 2^64) is h or h-1, which
+//    costs one more q of range (the compile-time bound tracker in kernels.cuh pays for it with a
+//    few extra top-bit reductions) and saves one of the four wide multiplies.
+//  SOLINAS (q = 2^60 - 2^14 + 1, the modulus of rtl/twiddle_*_4096_60bit.hex): h*q is formed with
+//    shifts and adds on the ALU pipe instead of 1 wide + 2 narrow multiplies.
+template <typename W> struct Growth;
+template <> struct Growth<uint32_t> { static constexpr int G = 2; };
+template <> struct Growth<uint64_t> { static constexpr int G = 3; };
+
+constexpr uint64_t kSolinasQ = (1ull << 60) - (1ull << 14) + 1;
+
+template <bool SOL> TNTT_HD uint32_t shoup_lazy(uint32_t y, uint32_t w, uint32_t wp, const Mod<uint32_t> &m) {
+    return shoup_mul(y, w, wp, m.nq);
+}
+template <bool SOL> TNTT_HD uint64_t shoup_lazy(uint64_t y, uint64_t w, uint64_t wp, const Mod<uint64_t> &m) {
+#if defined(__CUDA_ARCH__)
+    uint32_t y0, y1, w0, w1, p0, p1, h0, h1, lo, hi;
+    unpack64(y, y0, y1);
+    unpack64(w, w0, w1);
+    unpack64(wp, p0, p1);
+    asm("{\n\t.reg .u32 s0, s1, c;\n\t"
+        "mul.lo.u32 s0, %2, %5;\n\t"
+        "mul.hi.u32 s1, %2, %5;\n\t"
+        "mad.lo.cc.u32 s0, %3, %4, s0;\n\t"
+        "madc.hi.cc.u32 s1, %3, %4, s1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "mad.lo.cc.u32 %0, %3, %5, s1;\n\t"
+        "madc.hi.u32 %1, %3, %5, c;\n\t}"
+        : "=r"(h0), "=r"(h1) : "r"(y0), "r"(y1), "r"(p0), "r"(p1));
+    uint64_t acc;
+    if constexpr (SOL) {
+        uint32_t d0, d1;   // -h*q = (h << 14) - h - (h << 60)  (mod 2^64)
+        asm("{\n\t.reg .u32 t0, t1, t2;\n\t"
+            "shl.b32 t0, %2, 14;\n\t"
+            "shf.l.wrap.b32 t1, %2, %3, 14;\n\t"
+            "shl.b32 t2, %2, 28;\n\t"
+            "sub.cc.u32 %0, t0, %2;\n\t"
+            "subc.u32 %1, t1, %3;\n\t"
+            "sub.u32 %1, %1, t2;\n\t}"
+            : "=r"(d0), "=r"(d1) : "r"(h0), "r"(h1));
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(acc) : "r"(y0), "r"(w0), "l"(pack64(d0, d1)));
+        unpack64(acc, lo, hi);
+    } else {
+        uint32_t n0, n1;
+        unpack64(m.nq, n0, n1);
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(y0), "r"(w0));
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
+        unpack64(acc, lo, hi);
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h0), "r"(n1));
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(n0));
+    }
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y0), "r"(w1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y1), "r"(w0));
+    return pack64(lo, hi);
+#else
+    const uint32_t y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32), p0 = (uint32_t)wp, p1 = (uint32_t)(wp >> 32);
+    const unsigned __int128 mid = (unsigned __int128)((uint64_t)y0 * p1) + (uint64_t)y1 * p0;
+    const uint64_t h = (uint64_t)y1 * p1 + (uint64_t)(mid >> 32);
+    return y * w - h * m.q;   // identical for every q, also the Solinas one
+#endif
+}
+
+// Cooley-Tukey butterfly on lazy values: (x, y) <- (x + w*y, x - w*y + G*q).  y may be ANY word (the
+// product reduces it); the bound of both outputs is bound(x) + G*q.
+template <bool SOL, typename W> TNTT_HD void ct_butterfly(W &x, W &y, const Tw<W> &t, const Mod<W> &m) {
+    const W v = shoup_lazy<SOL>(y, t.w, t.wp, m);
+    TNTT_AUDIT_BUTTERFLY(x, v, m.qg);
+    y = x - v + m.qg;
     x = x + v;
 }
-// twiddle == 1: v must still be < 2q, so reduce y with the Shoup companion of 1 only when asked
-template <typename W> TNTT_HD void ct_butterfly_one(W &x, W &y, const Mod<W> &m) {
-    const W v = y - mulhi(y, m.one_p) * m.q;  // y mod q, in [0, 2q)
-    y = x - v + m.q2;
-    x = x + v;
+
+// Compile-time range bookkeeping, in units of 2^(BITS-4): every register entering butterfly stage number
+// `stage` (counted from the start of a transform whose inputs are below `b0` units) is below
+// bound_at(...) units.  With `red` set, a stage whose outputs could pass 16 units (= 2^BITS) first
+// applies csub_top() to its un-multiplied inputs, which brings them below 8 units (2^(BITS-1)).
+// Units are >= q because q < 2^(BITS-4) whenever `red` is used.
+TNTT_CX bool stage_needs_reduction(bool red, int g, int bound_in) { return red && bound_in + g > 16; }
+TNTT_CX int bound_after_stage(bool red, int g, int bound_in) {
+    return (stage_needs_reduction(red, g, bound_in) ? 8 : bound_in) + g;
+}
+TNTT_CX int bound_at(bool red, int g, int b0, int stage) {
+    int b = b0;
+    for (int s = 0; s < stage; ++s) b = bound_after_stage(red, g, b);
+    return b;
 }
 
 // Montgomery product x*y*2^-BITS mod q, result < x*y/2^BITS + q.

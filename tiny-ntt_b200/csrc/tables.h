@@ -68,7 +68,9 @@ template <typename W> inline Mod<W> make_mod(uint64_t q) {
     constexpr int BITS = WordTraits<W>::BITS;
     Mod<W> m;
     m.q = (W)q;
+    m.nq = (W)(0 - (W)q);
     m.q2 = (W)(2 * q);
+    m.qg = (W)(Growth<W>::G * q);
     m.top_sub = (W)((((u128)1 << (BITS - 1)) / q) * q);
     uint64_t inv = q;  // Newton: inv = q^-1 mod 2^64 (q odd)
     for (int i = 0; i < 6; ++i) inv *= 2 - q * inv;
@@ -131,19 +133,20 @@ template <typename W> inline std::vector<Tw<W>> scaled_powers(uint64_t root, uin
 }
 
 // Can all log n stages (plus the pointwise product) run without any intermediate reduction?
-//   forward: q(1 + 2 log n) <= 2^BITS ; Montgomery product r < fwd^2/2^BITS + q ; inverse: r + 2 q log n <= 2^BITS
+//   forward: q(1 + G log n) <= 2^BITS ; Montgomery product r < fwd^2/2^BITS + q ;
+//   inverse: r + G q log n <= 2^BITS ; standalone transforms start below 2q: q(2 + G log n) <= 2^BITS
 template <typename W> inline bool lazy_full_ok(uint64_t q, int logn) {
-    constexpr int BITS = WordTraits<W>::BITS;
+    constexpr int BITS = WordTraits<W>::BITS, G = Growth<W>::G;
     const u128 lim = (u128)1 << BITS;
-    const u128 fwd = (u128)q * (1 + 2 * logn);
+    const u128 fwd = (u128)q * (1 + G * logn);
     if (fwd > lim) return false;
     const u128 r = ((fwd >> 1) * (fwd >> 1) >> (BITS - 2)) + q + 4;  // >= fwd^2 / 2^BITS + q
-    return r + (u128)2 * logn * q <= lim && (u128)q * (2 + 2 * logn) <= lim;
+    return r + (u128)G * logn * q <= lim && (u128)q * (2 + G * logn) <= lim;
 }
-// Otherwise the top-bit reduction before every pass needs 2*logr*q <= 2^(BITS-1)
-template <typename W> inline bool lazy_pass_ok(uint64_t q, int logr) {
+// Otherwise the bound tracker of modarith.cuh (units of 2^(BITS-4)) needs q below one unit
+template <typename W> inline bool lazy_pass_ok(uint64_t q, int /*logr*/) {
     constexpr int BITS = WordTraits<W>::BITS;
-    return (u128)q * (2 * logr) <= ((u128)1 << (BITS - 1));
+    return q < ((uint64_t)1 << (BITS - 4));
 }
 
 }  // namespace host

@@ -55,7 +55,7 @@ def lib() -> C.CDLL:
     vp, sz, u64, u32, i = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
     L.tntt_plan_create.argtypes = [C.POINTER(vp), i, u32, u64, u64, i]
     L.tntt_plan_create_from_hex.argtypes = [C.POINTER(vp), i, u32, u64, C.c_char_p, C.c_char_p]
-    L.tntt_plan_write_hex.argtypes = [vp, C.c_char_p, i, i]
+    L.tntt_plan_write_hex.argtypes = [vp, C.c_char_p, i, i, i]
     L.tntt_plan_info_get.argtypes = [vp, C.POINTER(PlanInfo)]
     L.tntt_plan_destroy.argtypes = [vp]
     L.tntt_forward.argtypes = [vp, vp, vp, sz, i, vp]

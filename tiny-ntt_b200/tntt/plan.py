@@ -52,9 +52,11 @@ class Plan:
         check(lib().tntt_plan_info_get(h, C.byref(info)))
         return cls(h.value, info)
 
-    def write_hex(self, path: str, inverse: bool = False, hex_digits: Optional[int] = None) -> None:
+    def write_hex(self, path: str, inverse: bool = False, hex_digits: Optional[int] = None,
+                  uppercase: bool = True) -> None:
+        """psi^k (or psi^-k) in the $readmemh format of rtl/twiddle_*.hex."""
         digits = hex_digits or (6 if self.q < (1 << 24) else (self.q.bit_length() + 3) // 4)
-        check(lib().tntt_plan_write_hex(self._h, path.encode(), int(inverse), digits))
+        check(lib().tntt_plan_write_hex(self._h, path.encode(), int(inverse), digits, int(uppercase)))
 
     def close(self) -> None:
         if self._h:
