@@ -136,7 +136,8 @@ int tntt_polymul_variant(const tntt_plan *plan, int variant, const void *a, cons
 int tntt_plan_set_default_variant(tntt_plan *plan, int variant);
 
 /* Integer-pipe microbenchmark (measurement only): kind 0 = IMAD.LO, 1 = IMAD.WIDE.U32, 2 = IADD3,
- * 3 = 64-bit Shoup modmul chain, 4 = 32-bit Shoup modmul chain.  Returns thread-level ops per second. */
+ * 3 = exact 64-bit Shoup modmul chain, 4 = 32-bit Shoup modmul chain, 5 = the 64-bit butterfly product
+ * (approximate high product).  Returns thread-level ops per second. */
 int tntt_microbench(int device, int kind, double *ops_per_second);
 
 const char *tntt_last_error(void);

@@ -20,7 +20,7 @@ namespace tntt { long long g_range_violations = 0; }
 
 namespace {
 
-template <class C, int NA, bool RED, bool SOL = false> struct Emu {
+template <class C, int NA, bool RED> struct Emu {
     using W = typename C::W;
     static constexpr int T = C::THREADS;
     std::vector<W> tile;
@@ -45,7 +45,7 @@ template <class C, int NA, bool RED, bool SOL = false> struct Emu {
                     }
                 }
             }
-            for (int t = 0; t < T; ++t) fwd_pass<C, PASS, NA, RED, SOL>(X(t), t & (C::P - 1), tb, mod);
+            for (int t = 0; t < T; ++t) fwd_pass<C, PASS, NA, RED>(X(t), t & (C::P - 1), tb, mod);
             forward_from<PASS + 1>();
         }
     }
@@ -58,7 +58,7 @@ template <class C, int NA, bool RED, bool SOL = false> struct Emu {
                     tile_read<C, C::inv_lo(PASS)>(F(t), tile.data(), t >> C::LOGP, t & (C::P - 1));
                 }
             }
-            for (int t = 0; t < T; ++t) dit_pass<C, PASS, RED, SOL, IN_BND>(F(t), t & (C::P - 1), pyr, mod);
+            for (int t = 0; t < T; ++t) dit_pass<C, PASS, RED, IN_BND>(F(t), t & (C::P - 1), pyr, mod);
             dit_from<IN_BND, PASS + 1>(pyr);
         }
     }
@@ -140,9 +140,8 @@ template <class C, int NA, bool RED, bool SOL = false> struct Emu {
     }
 };
 
-template <class C, int NA, bool RED, bool SOL = false>
+template <class C, int NA, bool RED>
 int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q, uint64_t psi) {
-    if (SOL && q != kSolinasQ) return -3;
     using W = typename C::W;
     constexpr int BITS = WordTraits<W>::BITS;
     if (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN)) return -2;
@@ -152,7 +151,7 @@ int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q,
     auto inv = host::dit_pyramid<W>(host::modinv(omega, q), C::N, q);
     const uint64_t scale = host::mulmod(host::modinv(C::N % q, q), (uint64_t)((((host::u128)1) << BITS) % q), q);
     auto post = host::scaled_powers<W>(host::modinv(psi, q), scale, C::N, q);
-    Emu<C, NA, RED, SOL> e;
+    Emu<C, NA, RED> e;
     e.tb.fwd_pyr = fwd.data();
     e.tb.fwd_last = last.data();
     e.tb.post = post.data();
@@ -191,7 +190,7 @@ int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t 
 
 #define POLY_CASE(WB, WT, LN, LR, PPC, NA_, RED_)                                                      \
     if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && na == NA_ && red == RED_)       \
-        return run_polymul<Cfg<WT, LN, LR, PPC>, NA_, ((RED_ & 1) != 0), ((RED_ & 2) != 0)>(a, b, c, batch, q, psi);
+        return run_polymul<Cfg<WT, LN, LR, PPC>, NA_, (RED_ != 0)>(a, b, c, batch, q, psi);
 #define XFORM_CASE(WB, WT, LN, LR, PPC, RED_)                                                          \
     if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && red == RED_)                    \
         return run_transform<Cfg<WT, LN, LR, PPC>, (RED_ != 0)>(in, out, batch, q, root, mode, reduce_input);
@@ -223,10 +222,6 @@ int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, co
     POLY_CASE(8, uint64_t, 12, 4, 1, 2, 1)
     POLY_CASE(8, uint64_t, 12, 3, 1, 1, 1)
     POLY_CASE(8, uint64_t, 12, 3, 1, 2, 1)
-    POLY_CASE(8, uint64_t, 12, 4, 1, 1, 3)   // red | solinas
-    POLY_CASE(8, uint64_t, 12, 4, 1, 2, 3)
-    POLY_CASE(8, uint64_t, 12, 3, 1, 2, 3)
-    POLY_CASE(8, uint64_t, 8, 4, 16, 1, 3)
     return -1;
 }
 
@@ -256,7 +251,7 @@ int emu_slot(int word_bytes, int logn, int logr, int lo, int pl, int tid, int k)
 // arithmetic probes for tests/test_modarith.py
 uint64_t emu_shoup64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_mul(x, t.w, t.wp, (uint64_t)(0 - q)); }
 uint32_t emu_shoup32(uint32_t x, uint32_t w, uint32_t q) { auto t = host::make_tw<uint32_t>(w, q); return shoup_mul(x, t.w, t.wp, (uint32_t)(0u - q)); }
-uint64_t emu_shoup_lazy64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_lazy<false>(x, t.w, t.wp, host::make_mod<uint64_t>(q)); }
+uint64_t emu_shoup_lazy64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_lazy(x, t.w, t.wp, host::make_mod<uint64_t>(q)); }
 uint64_t emu_mont64(uint64_t x, uint64_t y, uint64_t q) { return mont_mul(x, y, host::make_mod<uint64_t>(q)); }
 uint32_t emu_mont32(uint32_t x, uint32_t y, uint32_t q) { return mont_mul(x, y, host::make_mod<uint32_t>(q)); }
 uint64_t emu_barrett64(uint64_t x, uint64_t y, uint64_t q) { return barrett_mul(x, y, host::make_mod<uint64_t>(q)); }

@@ -16,9 +16,7 @@ POLY = [(4, 8, 4, 16, 1, 0, "dilithium"), (4, 8, 4, 16, 2, 0, "dilithium"), (4, 
         (4, 12, 5, 2, 1, 0, "n4096_24"), (4, 12, 3, 1, 1, 0, "n4096_24"),
         (8, 12, 4, 1, 1, 1, "n4096_60"), (8, 12, 4, 1, 2, 1, "n4096_60"), (8, 12, 3, 1, 1, 1, "n4096_60"),
         (8, 12, 3, 1, 2, 1, "n4096_60"), (8, 12, 4, 1, 1, 0, "n4096_24"), (8, 8, 4, 16, 1, 0, "dilithium"),
-        (8, 8, 4, 16, 1, 1, "dilithium"), (8, 10, 4, 4, 1, 0, "n1024_24"), (8, 10, 4, 4, 1, 1, "n1024_24"),
-        # red | 2 = the Solinas (q = 2^60 - 2^14 + 1) specialisation
-        (8, 12, 4, 1, 1, 3, "n4096_60"), (8, 12, 4, 1, 2, 3, "n4096_60"), (8, 12, 3, 1, 2, 3, "n4096_60")]
+        (8, 8, 4, 16, 1, 1, "dilithium"), (8, 10, 4, 4, 1, 0, "n1024_24"), (8, 10, 4, 4, 1, 1, "n1024_24")]
 
 
 @pytest.fixture(scope="module")

@@ -142,8 +142,8 @@ template <typename W> int build_tables(tntt_plan *p) {
 int choose_default_variant(const tntt_plan *p) {
     // preference order measured on B200 (profiles/): first match wins
     static const char *prefer[] = {
-        "u64_n12_r4_p1_a2_red1_b2_s0_sol1", "u64_n12_r4_p1_a2_red1_b2_s0_sol0", "u64_n12_r4_p1_a1_red0_b2_s0_sol0",
-        "u32_n12_r4_p1_a1_red0_b4_s0_sol0", "u32_n10_r5_p8_a1_red0_b2_s0_sol0", "u32_n8_r4_p16_a2_red0_b4_s0_sol0",
+        "u64_n12_r4_p1_a1_red1_b3_s1", "u64_n12_r4_p1_a2_red1_b2_s0", "u64_n12_r4_p1_a1_red0_b2_s0",
+        "u32_n12_r4_p1_a1_red0_b4_s0", "u32_n10_r5_p8_a1_red0_b2_s0", "u32_n8_r4_p16_a2_red0_b4_s0",
     };
     const std::vector<PolymulVariant> &vs = all_variants();
     for (const char *name : prefer)
@@ -421,8 +421,8 @@ int tntt_variant_describe(int variant, char *buf, size_t buflen) {
     int occ = 0;
     const bool have = v.attributes(&attr, &occ) == cudaSuccess;
     if (!have) cudaGetLastError();
-    snprintf(buf, buflen, "%s word=%d n=%d r=%d ppc=%d na=%d red=%d sol=%d threads=%d smem=%zu regs=%d local=%zu ctas_per_sm=%d",
-             v.name, v.word_bytes, 1 << v.logn, 1 << v.logr, v.ppc, v.na, v.red, v.sol, v.threads, v.smem,
+    snprintf(buf, buflen, "%s word=%d n=%d r=%d ppc=%d na=%d red=%d threads=%d smem=%zu regs=%d local=%zu ctas_per_sm=%d",
+             v.name, v.word_bytes, 1 << v.logn, 1 << v.logr, v.ppc, v.na, v.red, v.threads, v.smem,
              have ? attr.numRegs : -1, have ? attr.localSizeBytes : (size_t)0, have ? occ : -1);
     return TNTT_OK;
 }
@@ -431,7 +431,6 @@ int tntt_variant_matches(const tntt_plan *p, int variant) {
     const PolymulVariant &v = all_variants()[variant];
     if (!p->info.has_psi || v.word_bytes != p->info.word_bytes || v.logn != (int)p->info.logn) return 0;
     if (v.red != p->info.lazy_reduce) return 0;
-    if (v.sol && p->info.q != kSolinasQ) return 0;
     if (v.red && !host::lazy_pass_ok<uint64_t>(p->info.q, v.logr)) return 0;
     return 1;
 }

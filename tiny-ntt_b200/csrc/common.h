@@ -12,7 +12,7 @@ namespace tntt {
 // one instantiation of the fused polymul kernel
 struct PolymulVariant {
     const char *name;
-    int word_bytes, logn, logr, ppc, na, red, sol, threads, minb;
+    int word_bytes, logn, logr, ppc, na, red, threads, minb;
     size_t smem;
     // tables / mod point at PolymulTables<W> / Mod<W> of the matching word type
     cudaError_t (*launch)(const void *a, const void *b, void *c, size_t batch, const void *tables, const void *mod,

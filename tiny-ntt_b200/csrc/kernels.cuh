@@ -39,6 +39,8 @@ template <typename W_, int LOGN_, int LOGR_, int PPC_> struct Cfg {
     static constexpr int PPC = PPC_, THREADS = P * PPC;
     static constexpr int NPASS = (LOGN + LOGR - 1) / LOGR;
     static constexpr int BANK_MASK = (1 << WordTraits<W>::BANK_BITS) - 1;
+    // per-thread twiddle tables are prefetched one pass ahead only when they are too big to stay in L1
+    static constexpr bool PREFETCH = (size_t)N * 2 * sizeof(W) >= 32768;
     static_assert(LOGN >= LOGR, "a thread cannot hold more than the polynomial");
     // forward pass p works on index bits [fwd_lo(p), fwd_bhi(p)), high bits first
     static TNTT_CX int fwd_lo(int p) { return cmax(LOGN - (p + 1) * LOGR, 0); }
@@ -136,7 +138,7 @@ template <class C, int KB> TNTT_HD void reduce_top_x(typename C::W (&x)[C::R], c
 // ---------------------------------------------------------------------------------------------
 // one stage (index bit B) of a forward pass; B is a template parameter so that every loop bound
 // below is a compile-time constant and the register arrays never fall into local memory
-template <class C, int PASS, int NA, bool RED, bool SOL, int B>
+template <class C, int PASS, int NA, bool RED, int B>
 TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                        const Mod<typename C::W> &mod) {
     using W = typename C::W;
@@ -161,10 +163,10 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
         for (int j = 0; j < NJ; ++j) {
             const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
 #pragma unroll
-            for (int a = 0; a < NA; ++a) ct_butterfly<SOL>(x[a][k0], x[a][k1], t, mod);
+            for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], t, mod);
         }
     }
-    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, SOL, B - 1>(x, tid, tb, mod);
+    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1>(x, tid, tb, mod);
 }
 // The last forward pass, the last inverse pass and the final scaling read per-thread-distinct
 // table entries (about N*16 B each, together more than L1 holds next to the tiles).  They are
@@ -189,10 +191,10 @@ template <class C> TNTT_HD void prefetch_post(int tid, const Tw<typename C::W> *
     for (int k = 0; k < C::R; ++k) prefetch_l1(&post[(k << C::LOGP) + tid]);
 }
 
-template <class C, int PASS, int NA, bool RED, bool SOL>
+template <class C, int PASS, int NA, bool RED>
 TNTT_HD void fwd_pass(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                       const Mod<typename C::W> &mod) {
-    fwd_stage<C, PASS, NA, RED, SOL, C::fwd_bhi(PASS) - 1>(x, tid, tb, mod);
+    fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1>(x, tid, tb, mod);
 }
 // bound (units of 2^(BITS-4)) of the spectrum a forward transform of canonical input leaves in registers
 template <class C, bool RED> TNTT_CX int fwd_out_bound() {
@@ -208,7 +210,7 @@ template <class C, bool RED> TNTT_CX int pointwise_out_bound() {
 // cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
 // ---------------------------------------------------------------------------------------------
 // IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
-template <class C, int PASS, bool RED, bool SOL, int IN_BND, int B>
+template <class C, int PASS, bool RED, int IN_BND, int B>
 TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
     using W = typename C::W;
     constexpr int LO = C::inv_lo(PASS);
@@ -224,14 +226,14 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
-            ct_butterfly<SOL>(x[k0], x[k1], t, mod);
+            ct_butterfly(x[k0], x[k1], t, mod);
         }
     }
-    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, SOL, IN_BND, B + 1>(x, tid, dt, mod);
+    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1>(x, tid, dt, mod);
 }
-template <class C, int PASS, bool RED, bool SOL, int IN_BND>
+template <class C, int PASS, bool RED, int IN_BND>
 TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
-    dit_stage<C, PASS, RED, SOL, IN_BND, C::inv_blo(PASS)>(x, tid, dt, mod);
+    dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS)>(x, tid, dt, mod);
 }
 
 // registers -> swizzled tile (layout with the register field at LO)
@@ -287,7 +289,7 @@ __device__ __forceinline__ void exchange(typename C::W (&x)[C::R], typename C::W
     tile_read<C, LO_TO>(x, tile, pl, tid);
 }
 
-template <class C, int NA, bool RED, bool SOL, int PASS = 0>
+template <class C, int NA, bool RED, int PASS = 0>
 __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typename C::W *tile, int pl, int tid,
                                             const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod) {
     if constexpr (PASS < C::NPASS) {
@@ -297,13 +299,13 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
                 exchange<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[a], tile + a * C::PPC * C::N, pl, tid);
             }
         }
-        if constexpr (PASS + 2 == C::NPASS) prefetch_fwd_last<C>(tid, tb);
-        fwd_pass<C, PASS, NA, RED, SOL>(x, tid, tb, mod);
-        forward_all<C, NA, RED, SOL, PASS + 1>(x, tile, pl, tid, tb, mod);
+        if constexpr (PASS + 2 == C::NPASS && C::PREFETCH) prefetch_fwd_last<C>(tid, tb);
+        fwd_pass<C, PASS, NA, RED>(x, tid, tb, mod);
+        forward_all<C, NA, RED, PASS + 1>(x, tile, pl, tid, tb, mod);
     }
 }
 
-template <class C, bool RED, bool SOL, int IN_BND, int PASS = 0>
+template <class C, bool RED, int IN_BND, int PASS = 0>
 __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid,
                                         const DitTables<typename C::W> &dt, const Tw<typename C::W> *post,
                                         const Mod<typename C::W> &mod) {
@@ -311,10 +313,10 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
         if constexpr (PASS > 0) {
             exchange<C, C::inv_lo(PASS - 1), C::inv_lo(PASS)>(x, tile, pl, tid);
         }
-        if constexpr (PASS + 2 == C::NPASS) prefetch_dit_last<C>(tid, dt.pyr);
-        if constexpr (PASS + 1 == C::NPASS) prefetch_post<C>(tid, post);
-        dit_pass<C, PASS, RED, SOL, IN_BND>(x, tid, dt, mod);
-        dit_all<C, RED, SOL, IN_BND, PASS + 1>(x, tile, pl, tid, dt, post, mod);
+        if constexpr (PASS + 2 == C::NPASS && C::PREFETCH) prefetch_dit_last<C>(tid, dt.pyr);
+        if constexpr (PASS + 1 == C::NPASS && C::PREFETCH) prefetch_post<C>(tid, post);
+        dit_pass<C, PASS, RED, IN_BND>(x, tid, dt, mod);
+        dit_all<C, RED, IN_BND, PASS + 1>(x, tile, pl, tid, dt, post, mod);
     }
 }
 
@@ -326,7 +328,7 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
 // ---------------------------------------------------------------------------------------------
 //   STASH = 1 (NA = 1 only): a's spectrum waits in a second shared tile instead of in registers while
 //              b is transformed (thread-private slots, [k][thread] order: no conflicts, no barrier)
-template <class C, int NA, bool RED, int MINB, int STASH = 0, bool SOL = false>
+template <class C, int NA, bool RED, int MINB, int STASH = 0>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
                size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
@@ -344,14 +346,14 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
         W x[1][C::R];
         W *stash = tile + C::PPC * C::N + threadIdx.x;
         row_load<C>(x[0], a + off, tid, active);
-        forward_all<C, 1, RED, SOL>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
             if constexpr (STASH) stash[k * C::THREADS] = x[0][k];
             else fa[k] = x[0][k];
         }
         row_load<C>(x[0], b + off, tid, active);
-        forward_all<C, 1, RED, SOL>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
             W u;
@@ -364,7 +366,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
         W x[2][C::R];
         row_load<C>(x[0], a + off, tid, active);
         row_load<C>(x[1], b + off, tid, active);
-        forward_all<C, 2, RED, SOL>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 2, RED>(x, tile, pl, tid, tb, mod);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
             W u = x[0][k];
@@ -372,7 +374,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
             fa[k] = mont_mul(u, x[1][k], mod);
         }
     }
-    dit_all<C, RED, SOL, pointwise_out_bound<C, RED>()>(fa, tile, pl, tid, tb.inv, tb.post, mod);
+    dit_all<C, RED, pointwise_out_bound<C, RED>()>(fa, tile, pl, tid, tb.inv, tb.post, mod);
     row_store_scaled<C>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
 }
 
@@ -405,7 +407,7 @@ transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict
     }
     __syncthreads();
     tile_read<C, 0>(x, tile, pl, tid);
-    dit_all<C, RED, false, 2>(x, tile, pl, tid, tb.dit, tb.post, mod);
+    dit_all<C, RED, 2>(x, tile, pl, tid, tb.dit, tb.post, mod);
     row_store_scaled<C>(x, out + off, tid, active, tb.post, tb.post_uniform, mod);
 }
 #endif  // __CUDACC__

@@ -16,7 +16,11 @@ template <int KIND> __global__ void __launch_bounds__(256) intpipe_kernel(uint32
 #pragma unroll
         for (int i = 0; i < kIlp; ++i) {
             if (KIND == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(m), "r"(b[i]));
-            if (KIND == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(m));
+            if (KIND == 1) {  // operands change every iteration, otherwise ptxas hoists the product out of the loop
+                uint32_t lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(w[i]));
+                asm("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(lo), "r"(hi));
+            }
             if (KIND == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
         }
     }
@@ -26,13 +30,13 @@ template <int KIND> __global__ void __launch_bounds__(256) intpipe_kernel(uint32
     if (r == 0x12345678u) sink[0] = r;
 }
 
-template <typename W> __global__ void __launch_bounds__(256) modmul_kernel(W *sink, W seed, Mod<W> mod, Tw<W> t) {
+template <typename W, bool LAZY> __global__ void __launch_bounds__(256) modmul_kernel(W *sink, W seed, Mod<W> mod, Tw<W> t) {
     W x[kIlp];
 #pragma unroll
     for (int i = 0; i < kIlp; ++i) x[i] = seed + threadIdx.x * 977u + i;
     for (int it = 0; it < kIters; ++it) {
 #pragma unroll
-        for (int i = 0; i < kIlp; ++i) x[i] = shoup_mul(x[i], t.w, t.wp, mod.nq);
+        for (int i = 0; i < kIlp; ++i) x[i] = LAZY ? shoup_lazy(x[i], t.w, t.wp, mod) : shoup_mul(x[i], t.w, t.wp, mod.nq);
     }
     W r = 0;
 #pragma unroll
@@ -51,7 +55,7 @@ cudaError_t run_microbench(int kind, double *ops_per_second) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    Mod<uint64_t> m64{}; m64.q = 1152921504606830593ull; m64.nq = 0 - m64.q;
+    Mod<uint64_t> m64{}; m64.q = 1152921504606830593ull; m64.nq = 0 - m64.q; m64.qg = 3 * m64.q;
     Mod<uint32_t> m32{}; m32.q = 8380417u; m32.nq = 0u - m32.q;
     Tw<uint64_t> t64{431606828070683274ull, 6905709249130932383ull};
     Tw<uint32_t> t32{1239911u, 635448320u};
@@ -62,8 +66,9 @@ cudaError_t run_microbench(int kind, double *ops_per_second) {
             case 0: intpipe_kernel<0><<<blocks, threads>>>((uint32_t *)sink, 12345u + rep); break;
             case 1: intpipe_kernel<1><<<blocks, threads>>>((uint32_t *)sink, 12345u + rep); break;
             case 2: intpipe_kernel<2><<<blocks, threads>>>((uint32_t *)sink, 12345u + rep); break;
-            case 3: modmul_kernel<uint64_t><<<blocks, threads>>>((uint64_t *)sink, 99ull + rep, m64, t64); break;
-            case 4: modmul_kernel<uint32_t><<<blocks, threads>>>((uint32_t *)sink, 99u + rep, m32, t32); break;
+            case 3: modmul_kernel<uint64_t, false><<<blocks, threads>>>((uint64_t *)sink, 99ull + rep, m64, t64); break;
+            case 5: modmul_kernel<uint64_t, true><<<blocks, threads>>>((uint64_t *)sink, 99ull + rep, m64, t64); break;
+            case 4: modmul_kernel<uint32_t, false><<<blocks, threads>>>((uint32_t *)sink, 99u + rep, m32, t32); break;
             default: cudaFree(sink); return cudaErrorInvalidValue;
         }
         cudaEventRecord(e1);

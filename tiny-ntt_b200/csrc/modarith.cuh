@@ -59,6 +59,9 @@ template <typename W> struct Mod {
     W nqinv;    // -q^-1 mod 2^BITS  (Montgomery)
     W one_p;    // floor(2^BITS / q) : Shoup companion of 1
     W mu;       // Barrett mu = floor(2^(2k)/q), k = bitlen(q)  (scripts/precompute_constants.py:30-55)
+    W zero;     // always 0.  Added as a third operand to two-input 64-bit additions: a three-input add can only
+                // issue as IADD3 on the ALU pipe, which stops ptxas from turning it into IMAD.X on the
+                // (already saturated) multiplier pipe.  It travels in the constant bank, so it costs nothing.
     int k;      // Barrett k
 };
 
@@ -143,18 +146,17 @@ template <typename W> inline void audit_butterfly(W x, W v, W qg) {
 //    product y0*p0 is dropped: h' = floor((y1*p1*2^64 + (y0*p1 + y1*p0)*2^32) / 2^64) is h or h-1, which
 //    costs one more q of range (the compile-time bound tracker in kernels.cuh pays for it with a
 //    few extra top-bit reductions) and saves one of the four wide multiplies.
-//  SOLINAS (q = 2^60 - 2^14 + 1, the modulus of rtl/twiddle_*_4096_60bit.hex): h*q is formed with
-//    shifts and adds on the ALU pipe instead of 1 wide + 2 narrow multiplies.
+//  (A variant forming h*q with shifts for q = 2^60 - 2^14 + 1 was measured slower -- 10.1 vs 11.3 M
+//   polymul/s -- because it trades 3 multiplies for ~8 ALU instructions and the kernel is issue-bound on
+//   that side; see DESIGN.md.)
 template <typename W> struct Growth;
 template <> struct Growth<uint32_t> { static constexpr int G = 2; };
 template <> struct Growth<uint64_t> { static constexpr int G = 3; };
 
-constexpr uint64_t kSolinasQ = (1ull << 60) - (1ull << 14) + 1;
-
-template <bool SOL> TNTT_HD uint32_t shoup_lazy(uint32_t y, uint32_t w, uint32_t wp, const Mod<uint32_t> &m) {
+TNTT_HD uint32_t shoup_lazy(uint32_t y, uint32_t w, uint32_t wp, const Mod<uint32_t> &m) {
     return shoup_mul(y, w, wp, m.nq);
 }
-template <bool SOL> TNTT_HD uint64_t shoup_lazy(uint64_t y, uint64_t w, uint64_t wp, const Mod<uint64_t> &m) {
+TNTT_HD uint64_t shoup_lazy(uint64_t y, uint64_t w, uint64_t wp, const Mod<uint64_t> &m) {
 #if defined(__CUDA_ARCH__)
     uint32_t y0, y1, w0, w1, p0, p1, h0, h1, lo, hi;
     unpack64(y, y0, y1);
@@ -169,28 +171,14 @@ template <bool SOL> TNTT_HD uint64_t shoup_lazy(uint64_t y, uint64_t w, uint64_t
         "mad.lo.cc.u32 %0, %3, %5, s1;\n\t"
         "madc.hi.u32 %1, %3, %5, c;\n\t}"
         : "=r"(h0), "=r"(h1) : "r"(y0), "r"(y1), "r"(p0), "r"(p1));
-    uint64_t acc;
-    if constexpr (SOL) {
-        uint32_t d0, d1;   // -h*q = (h << 14) - h - (h << 60)  (mod 2^64)
-        asm("{\n\t.reg .u32 t0, t1, t2;\n\t"
-            "shl.b32 t0, %2, 14;\n\t"
-            "shf.l.wrap.b32 t1, %2, %3, 14;\n\t"
-            "shl.b32 t2, %2, 28;\n\t"
-            "sub.cc.u32 %0, t0, %2;\n\t"
-            "subc.u32 %1, t1, %3;\n\t"
-            "sub.u32 %1, %1, t2;\n\t}"
-            : "=r"(d0), "=r"(d1) : "r"(h0), "r"(h1));
-        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(acc) : "r"(y0), "r"(w0), "l"(pack64(d0, d1)));
-        unpack64(acc, lo, hi);
-    } else {
-        uint32_t n0, n1;
-        unpack64(m.nq, n0, n1);
-        asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(y0), "r"(w0));
-        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
-        unpack64(acc, lo, hi);
-        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h0), "r"(n1));
-        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(n0));
-    }
+    uint32_t n0, n1;
+    unpack64(m.nq, n0, n1);
+    uint64_t acc;   // low 64 bits of y*w + h*nq: one IMAD.WIDE chain plus four IMAD.LO into the high word
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(y0), "r"(w0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
+    unpack64(acc, lo, hi);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h0), "r"(n1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(n0));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y0), "r"(w1));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y1), "r"(w0));
     return pack64(lo, hi);
@@ -198,17 +186,18 @@ template <bool SOL> TNTT_HD uint64_t shoup_lazy(uint64_t y, uint64_t w, uint64_t
     const uint32_t y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32), p0 = (uint32_t)wp, p1 = (uint32_t)(wp >> 32);
     const unsigned __int128 mid = (unsigned __int128)((uint64_t)y0 * p1) + (uint64_t)y1 * p0;
     const uint64_t h = (uint64_t)y1 * p1 + (uint64_t)(mid >> 32);
-    return y * w - h * m.q;   // identical for every q, also the Solinas one
+    return y * w - h * m.q;
 #endif
 }
 
 // Cooley-Tukey butterfly on lazy values: (x, y) <- (x + w*y, x - w*y + G*q).  y may be ANY word (the
 // product reduces it); the bound of both outputs is bound(x) + G*q.
-template <bool SOL, typename W> TNTT_HD void ct_butterfly(W &x, W &y, const Tw<W> &t, const Mod<W> &m) {
-    const W v = shoup_lazy<SOL>(y, t.w, t.wp, m);
+template <typename W> TNTT_HD void ct_butterfly(W &x, W &y, const Tw<W> &t, const Mod<W> &m) {
+    const W v = shoup_lazy(y, t.w, t.wp, m);
     TNTT_AUDIT_BUTTERFLY(x, v, m.qg);
     y = x - v + m.qg;
-    x = x + v;
+    if constexpr (sizeof(W) == 8) x = x + v + m.zero;
+    else x = x + v;
 }
 
 // Compile-time range bookkeeping, in units of 2^(BITS-4): every register entering butterfly stage number

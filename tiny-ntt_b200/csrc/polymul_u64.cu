@@ -16,12 +16,6 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 3, 1, 1, 1, 1),
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 3, 1, 2, 1, 1),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 12, 3, 1, 1, 1, 2, 1),
-    // q = 2^60 - 2^14 + 1 specialisations (h*q by shifts)
-    TNTT_POLYMUL_VARIANT_X(uint64_t, 64, 12, 4, 1, 1, 1, 2, 0, 1),
-    TNTT_POLYMUL_VARIANT_X(uint64_t, 64, 12, 4, 1, 2, 1, 2, 0, 1),
-    TNTT_POLYMUL_VARIANT_X(uint64_t, 64, 12, 4, 1, 1, 1, 3, 1, 1),
-    TNTT_POLYMUL_VARIANT_X(uint64_t, 64, 12, 3, 1, 2, 1, 2, 0, 1),
-    TNTT_POLYMUL_VARIANT_X(uint64_t, 64, 12, 3, 1, 2, 1, 1, 0, 1),
 };
 const PolymulVariant *polymul_variants_u64(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));

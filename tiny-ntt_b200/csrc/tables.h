@@ -77,6 +77,7 @@ template <typename W> inline Mod<W> make_mod(uint64_t q) {
     m.nqinv = (W)(0 - inv);
     m.one_p = (W)(((u128)1 << BITS) / q);
     m.k = bitlen(q);
+    m.zero = 0;
     m.mu = (W)(((u128)1 << (2 * m.k)) / q);
     return m;
 }
