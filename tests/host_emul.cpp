@@ -157,7 +157,7 @@ int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q,
     e.tb.post = post.data();
     e.tb.inv.pyr = inv.data();
     for (int i = 0; i < MAX_R && i < C::N; ++i) { e.tb.fwd_head[i] = fwd[i]; e.tb.inv.head[i] = inv[i]; }
-    e.mod = host::make_mod<W>(q);
+    e.mod = host::make_mod<W>(q, C::LOGN);
     e.polymul((const W *)a, (const W *)b, (W *)c, batch);
     return 0;
 }
@@ -181,7 +181,7 @@ int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t 
     tt.post_uniform = host::make_tw<W>(inverse ? n_inv : 1, q);
     tt.reduce_input = reduce_input;
     Emu<C, 1, RED> e;
-    e.mod = host::make_mod<W>(q);
+    e.mod = host::make_mod<W>(q, C::LOGN);
     e.transform((const W *)in, (W *)out, batch, tt);
     return 0;
 }

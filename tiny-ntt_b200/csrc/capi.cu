@@ -142,8 +142,8 @@ template <typename W> int build_tables(tntt_plan *p) {
 int choose_default_variant(const tntt_plan *p) {
     // preference order measured on B200 (profiles/): first match wins
     static const char *prefer[] = {
-        "u64_n12_r4_p1_a1_red1_b3_s1", "u64_n12_r4_p1_a2_red1_b2_s0", "u64_n12_r4_p1_a1_red0_b2_s0",
-        "u32_n12_r4_p1_a1_red0_b4_s0", "u32_n10_r5_p8_a1_red0_b2_s0", "u32_n8_r4_p16_a2_red0_b4_s0",
+        "u64_n12_r4_p1_a1_red1_b3_s1_t0", "u64_n12_r4_p1_a2_red1_b2_s0_t0", "u64_n12_r4_p1_a1_red0_b2_s0_t0",
+        "u32_n12_r4_p1_a1_red0_b4_s0_t0", "u32_n10_r5_p8_a1_red0_b2_s0_t0", "u32_n8_r4_p16_a2_red0_b4_s0_t0",
     };
     const std::vector<PolymulVariant> &vs = all_variants();
     for (const char *name : prefer)
@@ -190,8 +190,8 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
     // uint32 coefficients when the whole transform fits the lazy 32-bit range, else uint64
     I.word_bytes = host::lazy_full_ok<uint32_t>(q, (int)I.logn) ? 4 : 8;
     I.lazy_reduce = (I.word_bytes == 8 && !host::lazy_full_ok<uint64_t>(q, (int)I.logn)) ? 1 : 0;
-    p->mod32 = host::make_mod<uint32_t>(q < (1ull << 32) ? q : 3);
-    p->mod64 = host::make_mod<uint64_t>(q);
+    p->mod32 = host::make_mod<uint32_t>(q < (1ull << 32) ? q : 3, (int)I.logn);
+    p->mod64 = host::make_mod<uint64_t>(q, (int)I.logn);
     I.barrett_k = p->mod64.k;
     I.barrett_mu = p->mod64.mu;
     p->one_tw = host::make_tw<uint64_t>(1, q);

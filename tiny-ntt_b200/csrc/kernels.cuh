@@ -40,7 +40,11 @@ template <typename W_, int LOGN_, int LOGR_, int PPC_> struct Cfg {
     static constexpr int NPASS = (LOGN + LOGR - 1) / LOGR;
     static constexpr int BANK_MASK = (1 << WordTraits<W>::BANK_BITS) - 1;
     // per-thread twiddle tables are prefetched one pass ahead only when they are too big to stay in L1
+    #if defined(TNTT_FORCE_PREFETCH)
+    static constexpr bool PREFETCH = true;
+#else
     static constexpr bool PREFETCH = (size_t)N * 2 * sizeof(W) >= 32768;
+#endif
     static_assert(LOGN >= LOGR, "a thread cannot hold more than the polynomial");
     // forward pass p works on index bits [fwd_lo(p), fwd_bhi(p)), high bits first
     static TNTT_CX int fwd_lo(int p) { return cmax(LOGN - (p + 1) * LOGR, 0); }
@@ -133,14 +137,30 @@ template <class C, int KB> TNTT_HD void reduce_top_x(typename C::W (&x)[C::R], c
         if (!(k & (1 << KB))) x[k] = csub_top(x[k], mod.top_sub);
 }
 
+// twiddle pair from a shared-memory copy of a table (filled by a TMA bulk copy, see polymul_kernel)
+template <typename W> TNTT_HD Tw<W> ld_tw_shared(const Tw<W> *p) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(W) == 4) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        return Tw<W>{v.x, v.y};
+    } else {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+        return Tw<W>{v.x, v.y};
+    }
+#else
+    return *p;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // merged-psi Cooley-Tukey pass (natural -> bit-reversed), NA operands sharing each twiddle
 // ---------------------------------------------------------------------------------------------
 // one stage (index bit B) of a forward pass; B is a template parameter so that every loop bound
 // below is a compile-time constant and the register arrays never fall into local memory
-template <class C, int PASS, int NA, bool RED, int B>
+// STAB: non-null = shared-memory copy of fwd_last (only read when SMEM_TW)
+template <class C, int PASS, int NA, bool RED, int B, bool SMEM_TW = false>
 TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
-                       const Mod<typename C::W> &mod) {
+                       const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr) {
     using W = typename C::W;
     constexpr int LO = C::fwd_lo(PASS);
     constexpr int kb = B - LO;            // bit of the register index this stage pairs over
@@ -155,6 +175,8 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
         Tw<W> t;
         if constexpr (LO == C::LOGP && C::R <= MAX_R)  // first pass: same twiddle in every thread -> kernel parameter
             t = tb.fwd_head[(1 << s) + g];
+        else if constexpr (LO == 0 && SMEM_TW)  // last pass, table staged in shared memory by TMA
+            t = ld_tw_shared(&stab[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
         else if constexpr (LO == 0)  // last pass: every thread has its own twiddles -> transposed table, coalesced
             t = ld_tw(&tb.fwd_last[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
         else                    // middle passes: shared by 2^LO consecutive threads -> broadcast
@@ -166,7 +188,7 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
             for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], t, mod);
         }
     }
-    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1>(x, tid, tb, mod);
+    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1, SMEM_TW>(x, tid, tb, mod, stab);
 }
 // The last forward pass, the last inverse pass and the final scaling read per-thread-distinct
 // table entries (about N*16 B each, together more than L1 holds next to the tiles).  They are
@@ -191,10 +213,10 @@ template <class C> TNTT_HD void prefetch_post(int tid, const Tw<typename C::W> *
     for (int k = 0; k < C::R; ++k) prefetch_l1(&post[(k << C::LOGP) + tid]);
 }
 
-template <class C, int PASS, int NA, bool RED>
+template <class C, int PASS, int NA, bool RED, bool SMEM_TW = false>
 TNTT_HD void fwd_pass(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
-                      const Mod<typename C::W> &mod) {
-    fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1>(x, tid, tb, mod);
+                      const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr) {
+    fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1, SMEM_TW>(x, tid, tb, mod, stab);
 }
 // bound (units of 2^(BITS-4)) of the spectrum a forward transform of canonical input leaves in registers
 template <class C, bool RED> TNTT_CX int fwd_out_bound() {
@@ -210,18 +232,25 @@ template <class C, bool RED> TNTT_CX int pointwise_out_bound() {
 // cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
 // ---------------------------------------------------------------------------------------------
 // IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
-template <class C, int PASS, bool RED, int IN_BND, int B>
-TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
+template <class C, int PASS, bool RED, int IN_BND, int B, bool SMEM_TW = false>
+TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
+                       const Tw<typename C::W> *stab = nullptr) {
     using W = typename C::W;
     constexpr int LO = C::inv_lo(PASS);
     constexpr int kb = B - LO;
     constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
-    if constexpr (stage_needs_reduction(RED, Growth<W>::G, bound_at(RED, Growth<W>::G, IN_BND, B)))
+    if constexpr (B == 0 && dit_trivial_ok(RED, IN_BND)) {   // twiddle 1: no product at all
+#pragma unroll
+        for (int g = 0; g < NG; ++g) trivial_butterfly(x[2 * g], x[2 * g + 1], mod);
+    } else {
+    if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
         reduce_top_x<C, kb>(x, mod);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         Tw<W> t;
         if constexpr (LO == 0 && C::R <= MAX_R) t = dt.head[(1 << B) + j];  // first pass: uniform -> kernel parameter
+        else if constexpr (SMEM_TW && PASS + 1 == C::NPASS)   // last pass, pyr[2^blo ..) staged in shared memory by TMA
+            t = ld_tw_shared(&stab[(1 << B) - (1 << C::inv_blo(PASS)) + (j << LO) + (tid & ((1 << LO) - 1))]);
         else t = ld_tw(&dt.pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -229,11 +258,13 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
             ct_butterfly(x[k0], x[k1], t, mod);
         }
     }
-    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1>(x, tid, dt, mod);
+    }
+    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1, SMEM_TW>(x, tid, dt, mod, stab);
 }
-template <class C, int PASS, bool RED, int IN_BND>
-TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
-    dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS)>(x, tid, dt, mod);
+template <class C, int PASS, bool RED, int IN_BND, bool SMEM_TW = false>
+TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
+                      const Tw<typename C::W> *stab = nullptr) {
+    dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS), SMEM_TW>(x, tid, dt, mod, stab);
 }
 
 // registers -> swizzled tile (layout with the register field at LO)
@@ -277,6 +308,8 @@ TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row
     }
 }
 
+constexpr int kTwBufBytes = 65536;   // shared twiddle buffer of the TMA variants (+ 16 B for the mbarrier)
+
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------
 // regroup registers through the shared tile: layout LO_FROM -> LO_TO
@@ -289,9 +322,49 @@ __device__ __forceinline__ void exchange(typename C::W (&x)[C::R], typename C::W
     tile_read<C, LO_TO>(x, tile, pl, tid);
 }
 
-template <class C, int NA, bool RED, int PASS = 0>
+// ---------------------------------------------------------------------------------------------
+// TMA staging of the per-thread twiddle tables (TMA = 1 variants)
+//
+// The last forward pass, the last inverse pass and the final scaling read table entries that differ
+// per thread: 3 x 60 KB + 64 KB per polymul, more than L1 keeps next to the tiles, so plain loads pay
+// the L2 latency (ncu: long_scoreboard is a top stall).  Instead one thread issues a bulk async copy
+// (cp.async.bulk, the TMA engine; SASS UBLKCP) of the whole table into a 64 KB shared buffer while the
+// CTA computes the passes before it, and the CTA waits on an mbarrier just before the first use.
+// ---------------------------------------------------------------------------------------------
+struct TmaStage {
+    unsigned bar;     // shared address of the mbarrier
+    unsigned dst;     // shared address of the 64 KB table buffer
+    unsigned phase;   // parity of the next completion to wait for
+    __device__ __forceinline__ void init(void *bar_ptr, void *buf_ptr) {
+        bar = (unsigned)__cvta_generic_to_shared(bar_ptr);
+        dst = (unsigned)__cvta_generic_to_shared(buf_ptr);
+        phase = 0;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // thread 0 only; every thread must already be past its last read of the buffer (a barrier)
+    __device__ __forceinline__ void issue(const void *src, unsigned bytes) const {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+    __device__ __forceinline__ void wait() {
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                     "@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(phase) : "memory");
+        phase ^= 1u;
+    }
+};
+
+template <class C, int NA, bool RED, bool TMA, int PASS = 0>
 __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typename C::W *tile, int pl, int tid,
-                                            const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod) {
+                                            const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod,
+                                            TmaStage *tma = nullptr, const Tw<typename C::W> *stab = nullptr,
+                                            bool wait_table = false) {
     if constexpr (PASS < C::NPASS) {
         if constexpr (PASS > 0) {
 #pragma unroll
@@ -299,24 +372,38 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
                 exchange<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[a], tile + a * C::PPC * C::N, pl, tid);
             }
         }
-        if constexpr (PASS + 2 == C::NPASS && C::PREFETCH) prefetch_fwd_last<C>(tid, tb);
-        fwd_pass<C, PASS, NA, RED>(x, tid, tb, mod);
-        forward_all<C, NA, RED, PASS + 1>(x, tile, pl, tid, tb, mod);
+        if constexpr (PASS + 2 == C::NPASS && C::PREFETCH && !TMA) prefetch_fwd_last<C>(tid, tb);
+        if constexpr (TMA && PASS + 1 == C::NPASS) {
+            if (wait_table) tma->wait();
+        }
+        fwd_pass<C, PASS, NA, RED, TMA>(x, tid, tb, mod, stab);
+        forward_all<C, NA, RED, TMA, PASS + 1>(x, tile, pl, tid, tb, mod, tma, stab, wait_table);
     }
 }
 
-template <class C, bool RED, int IN_BND, int PASS = 0>
+// PF: prefetch the last pass's twiddles and the store table one pass ahead
+template <class C, bool RED, int IN_BND, bool TMA, bool PF, int PASS = 0>
 __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid,
                                         const DitTables<typename C::W> &dt, const Tw<typename C::W> *post,
-                                        const Mod<typename C::W> &mod) {
+                                        const Mod<typename C::W> &mod, TmaStage *tma = nullptr,
+                                        const Tw<typename C::W> *stab = nullptr) {
     if constexpr (PASS < C::NPASS) {
         if constexpr (PASS > 0) {
-            exchange<C, C::inv_lo(PASS - 1), C::inv_lo(PASS)>(x, tile, pl, tid);
+            __syncthreads();  // everybody is done reading the tile (and, for PASS 1, the forward twiddle buffer)
+            if constexpr (TMA && PASS == 1) {
+                constexpr int first = 1 << C::inv_blo(C::NPASS - 1);
+                if (threadIdx.x == 0)
+                    tma->issue(dt.pyr + first, (unsigned)((C::N - first) * sizeof(Tw<typename C::W>)));
+            }
+            tile_write<C, C::inv_lo(PASS - 1)>(x, tile, pl, tid);
+            __syncthreads();
+            tile_read<C, C::inv_lo(PASS)>(x, tile, pl, tid);
         }
-        if constexpr (PASS + 2 == C::NPASS && C::PREFETCH) prefetch_dit_last<C>(tid, dt.pyr);
-        if constexpr (PASS + 1 == C::NPASS && C::PREFETCH) prefetch_post<C>(tid, post);
-        dit_pass<C, PASS, RED, IN_BND>(x, tid, dt, mod);
-        dit_all<C, RED, IN_BND, PASS + 1>(x, tile, pl, tid, dt, post, mod);
+        if constexpr (PASS + 2 == C::NPASS && PF && !TMA) prefetch_dit_last<C>(tid, dt.pyr);
+        if constexpr (PASS + 1 == C::NPASS && PF) prefetch_post<C>(tid, post);
+        if constexpr (TMA && PASS + 1 == C::NPASS) tma->wait();
+        dit_pass<C, PASS, RED, IN_BND, TMA>(x, tid, dt, mod, stab);
+        dit_all<C, RED, IN_BND, TMA, PF, PASS + 1>(x, tile, pl, tid, dt, post, mod, tma, stab);
     }
 }
 
@@ -328,7 +415,8 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
 // ---------------------------------------------------------------------------------------------
 //   STASH = 1 (NA = 1 only): a's spectrum waits in a second shared tile instead of in registers while
 //              b is transformed (thread-private slots, [k][thread] order: no conflicts, no barrier)
-template <class C, int NA, bool RED, int MINB, int STASH = 0>
+//   TMA = 1: the per-thread twiddle tables are staged in shared memory by bulk async copies (see TmaStage)
+template <class C, int NA, bool RED, int MINB, int STASH = 0, int TMA = 0>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
                size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
@@ -341,19 +429,32 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     const bool active = poly < batch;
     const size_t off = active ? poly * C::N : 0;
 
+    // shared memory: [NA tiles][stash tile][64 KB twiddle buffer][mbarrier]
+    TmaStage tma_s;
+    TmaStage *tma = nullptr;
+    const Tw<W> *stab = nullptr;
+    if constexpr (TMA) {
+        static_assert(C::NPASS >= 3 && C::PPC == 1, "TMA staging is built for the three-pass, one-polynomial-per-CTA shapes");
+        unsigned char *buf = smem_raw + (size_t)(NA + STASH) * C::PPC * C::N * sizeof(W);
+        tma_s.init(buf + kTwBufBytes, buf);
+        tma = &tma_s;
+        stab = reinterpret_cast<const Tw<W> *>(buf);
+        if (threadIdx.x == 0) tma->issue(tb.fwd_last, (unsigned)(C::FWD_LAST_ENTRIES * sizeof(Tw<W>)));
+    }
+
     W fa[C::R];
     if constexpr (NA == 1) {
         W x[1][C::R];
         W *stash = tile + C::PPC * C::N + threadIdx.x;
         row_load<C>(x[0], a + off, tid, active);
-        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 1, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, true);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
             if constexpr (STASH) stash[k * C::THREADS] = x[0][k];
             else fa[k] = x[0][k];
         }
         row_load<C>(x[0], b + off, tid, active);
-        forward_all<C, 1, RED>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 1, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, false);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
             W u;
@@ -366,7 +467,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
         W x[2][C::R];
         row_load<C>(x[0], a + off, tid, active);
         row_load<C>(x[1], b + off, tid, active);
-        forward_all<C, 2, RED>(x, tile, pl, tid, tb, mod);
+        forward_all<C, 2, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, true);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
             W u = x[0][k];
@@ -374,7 +475,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
             fa[k] = mont_mul(u, x[1][k], mod);
         }
     }
-    dit_all<C, RED, pointwise_out_bound<C, RED>()>(fa, tile, pl, tid, tb.inv, tb.post, mod);
+    dit_all<C, RED, pointwise_out_bound<C, RED>(), (TMA != 0), C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod, tma, stab);
     row_store_scaled<C>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
 }
 
@@ -407,7 +508,7 @@ transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict
     }
     __syncthreads();
     tile_read<C, 0>(x, tile, pl, tid);
-    dit_all<C, RED, 2>(x, tile, pl, tid, tb.dit, tb.post, mod);
+    dit_all<C, RED, 2, false, true>(x, tile, pl, tid, tb.dit, tb.post, mod);   // short kernel: latency-bound without it (measured 2x)
     row_store_scaled<C>(x, out + off, tid, active, tb.post, tb.post_uniform, mod);
 }
 #endif  // __CUDACC__

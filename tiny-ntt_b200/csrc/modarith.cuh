@@ -59,6 +59,7 @@ template <typename W> struct Mod {
     W nqinv;    // -q^-1 mod 2^BITS  (Montgomery)
     W one_p;    // floor(2^BITS / q) : Shoup companion of 1
     W mu;       // Barrett mu = floor(2^(2k)/q), k = bitlen(q)  (scripts/precompute_constants.py:30-55)
+    W triv_c;   // multiple of q added by the multiplication-free first DIT stage: >= the bound of that stage's inputs
     W zero;     // always 0.  Added as a third operand to two-input 64-bit additions: a three-input add can only
                 // issue as IADD3 on the ALU pipe, which stops ptxas from turning it into IMAD.X on the
                 // (already saturated) multiplier pipe.  It travels in the constant bank, so it costs nothing.
@@ -200,6 +201,20 @@ template <typename W> TNTT_HD void ct_butterfly(W &x, W &y, const Tw<W> &t, cons
     else x = x + v;
 }
 
+// First stage of a decimation-in-time transform: its twiddle is 1, so no product is needed, only
+// (x, y) <- (x + y, x - y + c) with c = m.triv_c, a multiple of q that is >= y.
+template <typename W> TNTT_HD void trivial_butterfly(W &x, W &y, const Mod<W> &m) {
+#if !defined(__CUDA_ARCH__) && defined(TNTT_AUDIT_RANGES)
+    {
+        const unsigned __int128 lim = (unsigned __int128)1 << WordTraits<W>::BITS;
+        if ((unsigned __int128)x + y >= lim || y > m.triv_c || (unsigned __int128)x + m.triv_c >= lim + y) ++g_range_violations;
+    }
+#endif
+    const W s = x + y;
+    y = x - y + m.triv_c;
+    x = s;
+}
+
 // Compile-time range bookkeeping, in units of 2^(BITS-4): every register entering butterfly stage number
 // `stage` (counted from the start of a transform whose inputs are below `b0` units) is below
 // bound_at(...) units.  With `red` set, a stage whose outputs could pass 16 units (= 2^BITS) first
@@ -212,6 +227,20 @@ TNTT_CX int bound_after_stage(bool red, int g, int bound_in) {
 TNTT_CX int bound_at(bool red, int g, int b0, int stage) {
     int b = b0;
     for (int s = 0; s < stage; ++s) b = bound_after_stage(red, g, b);
+    return b;
+}
+// DIT transforms whose first stage is multiplication-free: that stage takes inputs below b0 <= 7 units to
+// outputs below b0 + 8 (x + y < 2 b0; x - y + triv_c with triv_c < 8 units).
+constexpr int kTrivMaxIn = 7;
+#if defined(TNTT_NO_TRIVIAL)
+TNTT_CX bool dit_trivial_ok(bool, int) { return false; }
+#else
+TNTT_CX bool dit_trivial_ok(bool red, int b0) { return !red || b0 <= kTrivMaxIn; }
+#endif
+TNTT_CX int dit_bound_at(bool red, int g, int b0, int stage) {
+    if (!dit_trivial_ok(red, b0) || stage == 0) return bound_at(red, g, b0, stage);
+    int b = b0 + 8;
+    for (int s = 1; s < stage; ++s) b = bound_after_stage(red, g, b);
     return b;
 }
 

@@ -4,38 +4,39 @@
 
 namespace tntt {
 
-template <class C, int NA, bool RED, int MINB, int STASH = 0> struct PolymulInst {
+template <class C, int NA, bool RED, int MINB, int STASH = 0, int TMA = 0> struct PolymulInst {
     using W = typename C::W;
-    static constexpr size_t SMEM = (size_t)(NA + STASH) * C::PPC * C::N * sizeof(W);
+    static constexpr size_t SMEM = (size_t)(NA + STASH) * C::PPC * C::N * sizeof(W) + (TMA ? kTwBufBytes + 16 : 0);
     static cudaError_t launch(const void *a, const void *b, void *c, size_t batch, const void *tables, const void *mod,
                               cudaStream_t stream) {
         if (batch == 0) return cudaSuccess;
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
-        polymul_kernel<C, NA, RED, MINB, STASH><<<(unsigned)ctas, C::THREADS, SMEM, stream>>>(
+        polymul_kernel<C, NA, RED, MINB, STASH, TMA><<<(unsigned)ctas, C::THREADS, SMEM, stream>>>(
             static_cast<const W *>(a), static_cast<const W *>(b), static_cast<W *>(c), batch,
             *static_cast<const PolymulTables<W> *>(tables), *static_cast<const Mod<W> *>(mod));
         return cudaGetLastError();
     }
     static cudaError_t prepare() {
-        return cudaFuncSetAttribute(polymul_kernel<C, NA, RED, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        return cudaFuncSetAttribute(polymul_kernel<C, NA, RED, MINB, STASH, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)SMEM);
     }
     static cudaError_t attributes(cudaFuncAttributes *attr, int *blocks_per_sm) {
-        cudaError_t e = cudaFuncGetAttributes(attr, polymul_kernel<C, NA, RED, MINB, STASH>);
+        cudaError_t e = cudaFuncGetAttributes(attr, polymul_kernel<C, NA, RED, MINB, STASH, TMA>);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, polymul_kernel<C, NA, RED, MINB, STASH>,
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, polymul_kernel<C, NA, RED, MINB, STASH, TMA>,
                                                              C::THREADS, SMEM);
     }
 };
 
-#define TNTT_POLYMUL_VARIANT(WT, WB, LN, LR, PPC, NA, RED, MINB) TNTT_POLYMUL_VARIANT_S(WT, WB, LN, LR, PPC, NA, RED, MINB, 0)
-#define TNTT_POLYMUL_VARIANT_S(WT, WB, LN, LR, PPC, NA, RED, MINB, ST)                                              \
+#define TNTT_POLYMUL_VARIANT(WT, WB, LN, LR, PPC, NA, RED, MINB) TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, 0, 0)
+#define TNTT_POLYMUL_VARIANT_S(WT, WB, LN, LR, PPC, NA, RED, MINB, ST) TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, ST, 0)
+#define TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, ST, TM)                                              \
     PolymulVariant {                                                                                          \
-        "u" #WB "_n" #LN "_r" #LR "_p" #PPC "_a" #NA "_red" #RED "_b" #MINB "_s" #ST, WB / 8, LN, LR, PPC, NA, RED,     \
-            Cfg<WT, LN, LR, PPC>::THREADS, MINB, PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST>::SMEM, \
-            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST>::launch,                                 \
-            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST>::prepare,                                \
-            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST>::attributes                              \
+        "u" #WB "_n" #LN "_r" #LR "_p" #PPC "_a" #NA "_red" #RED "_b" #MINB "_s" #ST "_t" #TM, WB / 8, LN, LR, PPC, NA, RED,     \
+            Cfg<WT, LN, LR, PPC>::THREADS, MINB, PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::SMEM, \
+            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::launch,                                 \
+            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::prepare,                                \
+            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::attributes                              \
     }
 
 }  // namespace tntt

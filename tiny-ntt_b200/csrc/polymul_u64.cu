@@ -16,6 +16,10 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 3, 1, 1, 1, 1),
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 3, 1, 2, 1, 1),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 12, 3, 1, 1, 1, 2, 1),
+    // per-thread twiddle tables staged in shared memory by TMA bulk copies
+    TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 1, 1, 2, 0, 1),
+    TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 1, 1, 1, 1, 1),
+    TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 2, 1, 1, 0, 1),
 };
 const PolymulVariant *polymul_variants_u64(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));

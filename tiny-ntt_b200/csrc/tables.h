@@ -64,7 +64,10 @@ template <typename W> inline Tw<W> make_tw(uint64_t w, uint64_t q) {
     return Tw<W>{(W)w, (W)((((u128)w) << BITS) / q)};
 }
 
-template <typename W> inline Mod<W> make_mod(uint64_t q) {
+template <typename W> inline bool lazy_full_ok(uint64_t q, int logn);
+
+// `logn` selects the constant of the multiplication-free first inverse stage (Mod::triv_c)
+template <typename W> inline Mod<W> make_mod(uint64_t q, int logn = 12) {
     constexpr int BITS = WordTraits<W>::BITS;
     Mod<W> m;
     m.q = (W)q;
@@ -78,6 +81,16 @@ template <typename W> inline Mod<W> make_mod(uint64_t q) {
     m.one_p = (W)(((u128)1 << BITS) / q);
     m.k = bitlen(q);
     m.zero = 0;
+    if (lazy_full_ok<W>(q, logn)) {   // inputs of the first inverse stage are below r = fwd^2/2^BITS + q (or 2q)
+        const u128 fwd = (u128)q * (1 + Growth<W>::G * logn);
+        const u128 r = ((fwd >> 1) * (fwd >> 1) >> (BITS - 2)) + q + 4;
+        u128 mult = (r + q - 1) / q;
+        if (mult < 2) mult = 2;
+        m.triv_c = (W)(mult * q);
+    } else {                          // tracked in units of 2^(BITS-4): inputs below 7 units
+        const u128 seven = (u128)kTrivMaxIn << (BITS - 4);
+        m.triv_c = (W)(((seven + q - 1) / q) * q);
+    }
     m.mu = (W)(((u128)1 << (2 * m.k)) / q);
     return m;
 }
@@ -142,7 +155,9 @@ template <typename W> inline bool lazy_full_ok(uint64_t q, int logn) {
     const u128 fwd = (u128)q * (1 + G * logn);
     if (fwd > lim) return false;
     const u128 r = ((fwd >> 1) * (fwd >> 1) >> (BITS - 2)) + q + 4;  // >= fwd^2 / 2^BITS + q
-    return r + (u128)G * logn * q <= lim && (u128)q * (2 + G * logn) <= lim;
+    // first inverse stage is multiplication-free: (x + y, x - y + c), c = ceil(r/q) q  ->  below 2r + q
+    const u128 after_first = 2 * r + q;
+    return after_first + (u128)G * (logn - 1) * q <= lim && (u128)q * (4 + G * (logn - 1)) <= lim;
 }
 // Otherwise the bound tracker of modarith.cuh (units of 2^(BITS-4)) needs q below one unit
 template <typename W> inline bool lazy_pass_ok(uint64_t q, int /*logr*/) {
