@@ -9,9 +9,11 @@ from ._lib import LIB_PATH, SYMBOLS, TnttError, lib  # noqa: F401
 from .ops import (as_tensor, bit_reverse, butterfly_lanes, cg_stage, forward, inverse, microbench, pointwise,  # noqa: F401
                   polymul, polymul_host, reduce, scale)
 from .plan import Plan, clear_plan_cache, get_plan  # noqa: F401
+from .rns import RnsContext, find_psi  # noqa: F401
 from .shard import shard_range, shard_rows  # noqa: F401
 
 __all__ = [
     "Plan", "get_plan", "clear_plan_cache", "forward", "inverse", "pointwise", "polymul", "polymul_host", "cg_stage",
     "bit_reverse", "scale", "reduce", "butterfly_lanes", "microbench", "shard_range", "shard_rows", "TnttError", "lib",
+    "RnsContext", "find_psi",
 ]
