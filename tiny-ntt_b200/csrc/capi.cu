@@ -143,7 +143,7 @@ int choose_default_variant(const tntt_plan *p) {
     // preference order measured on B200 (profiles/): first match wins
     static const char *prefer[] = {
         "u64_n12_r4_p1_a1_red1_b3_s1_t0", "u64_n12_r4_p1_a2_red1_b2_s0_t0", "u64_n12_r4_p1_a1_red0_b2_s0_t0",
-        "u32_n12_r4_p1_a1_red0_b4_s0_t0", "u32_n10_r5_p8_a1_red0_b2_s0_t0", "u32_n8_r4_p16_a2_red0_b4_s0_t0",
+        "u32_n12_r4_p1_a2_red0_b4_s0_t0", "u32_n10_r5_p8_a2_red0_b2_s0_t0", "u32_n8_r4_p16_a2_red0_b4_s0_t0",
     };
     const std::vector<PolymulVariant> &vs = all_variants();
     for (const char *name : prefer)
@@ -470,8 +470,8 @@ int tntt_polymul_host(tntt_plan *p, const void *a, const void *b, void *c, size_
     DeviceSetter ds(p->info.device);
     std::lock_guard<std::mutex> lock(p->pipe_mu);
     const size_t row_bytes = (size_t)p->info.n * p->info.word_bytes;
-    // chunk: ~32 MiB per operand, at least one row
-    size_t rows = (32u << 20) / row_bytes;
+    // chunk: ~8 MiB per operand (short pipeline fill/drain, still >= 256 rows of the largest polynomial)
+    size_t rows = (8u << 20) / row_bytes;
     if (rows < 1) rows = 1;
     if (rows > batch) rows = batch;
     if (p->pipe_rows < rows) {

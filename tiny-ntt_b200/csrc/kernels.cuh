@@ -158,9 +158,12 @@ template <typename W> TNTT_HD Tw<W> ld_tw_shared(const Tw<W> *p) {
 // one stage (index bit B) of a forward pass; B is a template parameter so that every loop bound
 // below is a compile-time constant and the register arrays never fall into local memory
 // STAB: non-null = shared-memory copy of fwd_last (only read when SMEM_TW)
-template <class C, int PASS, int NA, bool RED, int B, bool SMEM_TW = false>
+// PRE: the twiddle of the pass's first stage was loaded before the tile exchange (pre_t), so its
+// latency overlaps the barriers instead of following them
+template <class C, int PASS, int NA, bool RED, int B, bool SMEM_TW = false, bool PRE = false>
 TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
-                       const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr) {
+                       const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr,
+                       const Tw<typename C::W> *pre_t = nullptr) {
     using W = typename C::W;
     constexpr int LO = C::fwd_lo(PASS);
     constexpr int kb = B - LO;            // bit of the register index this stage pairs over
@@ -173,7 +176,9 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         Tw<W> t;
-        if constexpr (LO == C::LOGP && C::R <= MAX_R)  // first pass: same twiddle in every thread -> kernel parameter
+        if constexpr (PRE && B == C::fwd_bhi(PASS) - 1 && NG == 1)
+            t = *pre_t;
+        else if constexpr (LO == C::LOGP && C::R <= MAX_R)  // first pass: same twiddle in every thread -> kernel parameter
             t = tb.fwd_head[(1 << s) + g];
         else if constexpr (LO == 0 && SMEM_TW)  // last pass, table staged in shared memory by TMA
             t = ld_tw_shared(&stab[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
@@ -188,7 +193,13 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
             for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], t, mod);
         }
     }
-    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1, SMEM_TW>(x, tid, tb, mod, stab);
+    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1, SMEM_TW, PRE>(x, tid, tb, mod, stab, pre_t);
+}
+// the single twiddle of the first stage of forward pass PASS (valid when that pass runs all log2 R stages)
+template <class C, int PASS> TNTT_HD Tw<typename C::W> fwd_first_twiddle(int tid, const PolymulTables<typename C::W> &tb) {
+    constexpr int LO = C::fwd_lo(PASS), B = C::fwd_bhi(PASS) - 1, s = C::LOGN - 1 - B;
+    if constexpr (LO == 0) return ld_tw(&tb.fwd_last[tid]);
+    else return ld_tw(&tb.fwd_pyr[(1 << s) + (tid >> LO)]);
 }
 // The last forward pass, the last inverse pass and the final scaling read per-thread-distinct
 // table entries (about N*16 B each, together more than L1 holds next to the tiles).  They are
@@ -213,10 +224,11 @@ template <class C> TNTT_HD void prefetch_post(int tid, const Tw<typename C::W> *
     for (int k = 0; k < C::R; ++k) prefetch_l1(&post[(k << C::LOGP) + tid]);
 }
 
-template <class C, int PASS, int NA, bool RED, bool SMEM_TW = false>
+template <class C, int PASS, int NA, bool RED, bool SMEM_TW = false, bool PRE = false>
 TNTT_HD void fwd_pass(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
-                      const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr) {
-    fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1, SMEM_TW>(x, tid, tb, mod, stab);
+                      const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr,
+                      const Tw<typename C::W> *pre_t = nullptr) {
+    fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1, SMEM_TW, PRE>(x, tid, tb, mod, stab, pre_t);
 }
 // bound (units of 2^(BITS-4)) of the spectrum a forward transform of canonical input leaves in registers
 template <class C, bool RED> TNTT_CX int fwd_out_bound() {
@@ -232,9 +244,9 @@ template <class C, bool RED> TNTT_CX int pointwise_out_bound() {
 // cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
 // ---------------------------------------------------------------------------------------------
 // IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
-template <class C, int PASS, bool RED, int IN_BND, int B, bool SMEM_TW = false>
+template <class C, int PASS, bool RED, int IN_BND, int B, bool SMEM_TW = false, bool PRE = false>
 TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
-                       const Tw<typename C::W> *stab = nullptr) {
+                       const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
     using W = typename C::W;
     constexpr int LO = C::inv_lo(PASS);
     constexpr int kb = B - LO;
@@ -248,7 +260,8 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         Tw<W> t;
-        if constexpr (LO == 0 && C::R <= MAX_R) t = dt.head[(1 << B) + j];  // first pass: uniform -> kernel parameter
+        if constexpr (PRE && B == C::inv_blo(PASS) && NJ == 1) t = *pre_t;
+        else if constexpr (LO == 0 && C::R <= MAX_R) t = dt.head[(1 << B) + j];  // first pass: uniform -> kernel parameter
         else if constexpr (SMEM_TW && PASS + 1 == C::NPASS)   // last pass, pyr[2^blo ..) staged in shared memory by TMA
             t = ld_tw_shared(&stab[(1 << B) - (1 << C::inv_blo(PASS)) + (j << LO) + (tid & ((1 << LO) - 1))]);
         else t = ld_tw(&dt.pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
@@ -259,12 +272,17 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
         }
     }
     }
-    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1, SMEM_TW>(x, tid, dt, mod, stab);
+    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1, SMEM_TW, PRE>(x, tid, dt, mod, stab, pre_t);
 }
-template <class C, int PASS, bool RED, int IN_BND, bool SMEM_TW = false>
+template <class C, int PASS, bool RED, int IN_BND, bool SMEM_TW = false, bool PRE = false>
 TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
-                      const Tw<typename C::W> *stab = nullptr) {
-    dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS), SMEM_TW>(x, tid, dt, mod, stab);
+                      const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
+    dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS), SMEM_TW, PRE>(x, tid, dt, mod, stab, pre_t);
+}
+// the single twiddle of the first stage of inverse pass PASS (valid when its register field starts at that bit)
+template <class C, int PASS> TNTT_HD Tw<typename C::W> dit_first_twiddle(int tid, const DitTables<typename C::W> &dt) {
+    constexpr int LO = C::inv_lo(PASS), B = C::inv_blo(PASS);
+    return ld_tw(&dt.pyr[(1 << B) + (tid & ((1 << LO) - 1))]);
 }
 
 // registers -> swizzled tile (layout with the register field at LO)
@@ -366,6 +384,10 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
                                             TmaStage *tma = nullptr, const Tw<typename C::W> *stab = nullptr,
                                             bool wait_table = false) {
     if constexpr (PASS < C::NPASS) {
+        // first-stage twiddle of this pass: issue the load before the barriers of the exchange
+        constexpr bool PRE = PASS > 0 && (C::fwd_bhi(PASS) - C::fwd_lo(PASS) == C::LOGR) && !(TMA && PASS + 1 == C::NPASS);
+        Tw<typename C::W> t0{};
+        if constexpr (PRE) t0 = fwd_first_twiddle<C, PASS>(tid, tb);
         if constexpr (PASS > 0) {
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
@@ -376,7 +398,7 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
         if constexpr (TMA && PASS + 1 == C::NPASS) {
             if (wait_table) tma->wait();
         }
-        fwd_pass<C, PASS, NA, RED, TMA>(x, tid, tb, mod, stab);
+        fwd_pass<C, PASS, NA, RED, TMA, PRE>(x, tid, tb, mod, stab, &t0);
         forward_all<C, NA, RED, TMA, PASS + 1>(x, tile, pl, tid, tb, mod, tma, stab, wait_table);
     }
 }
@@ -388,6 +410,9 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
                                         const Mod<typename C::W> &mod, TmaStage *tma = nullptr,
                                         const Tw<typename C::W> *stab = nullptr) {
     if constexpr (PASS < C::NPASS) {
+        constexpr bool PRE = PASS > 0 && C::inv_lo(PASS) == C::inv_blo(PASS) && !(TMA && PASS + 1 == C::NPASS);
+        Tw<typename C::W> t0{};
+        if constexpr (PRE) t0 = dit_first_twiddle<C, PASS>(tid, dt);
         if constexpr (PASS > 0) {
             __syncthreads();  // everybody is done reading the tile (and, for PASS 1, the forward twiddle buffer)
             if constexpr (TMA && PASS == 1) {
@@ -402,7 +427,7 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
         if constexpr (PASS + 2 == C::NPASS && PF && !TMA) prefetch_dit_last<C>(tid, dt.pyr);
         if constexpr (PASS + 1 == C::NPASS && PF) prefetch_post<C>(tid, post);
         if constexpr (TMA && PASS + 1 == C::NPASS) tma->wait();
-        dit_pass<C, PASS, RED, IN_BND, TMA>(x, tid, dt, mod, stab);
+        dit_pass<C, PASS, RED, IN_BND, TMA, PRE>(x, tid, dt, mod, stab, &t0);
         dit_all<C, RED, IN_BND, TMA, PF, PASS + 1>(x, tile, pl, tid, dt, post, mod, tma, stab);
     }
 }
