@@ -104,7 +104,7 @@ int tntt_pointwise(const tntt_plan *plan, const void *a, const void *b, void *c,
  * one HBM round trip per polynomial. */
 int tntt_polymul(const tntt_plan *plan, const void *a, const void *b, void *c, size_t batch, void *cuda_stream);
 
-/* Same through HOST buffers (pinned for full overlap): 8 MiB chunks, H2D -> kernel -> D2H over three
+/* Same through HOST buffers (pinned for full overlap): 32 MiB chunks, H2D -> kernel -> D2H over three
  * streams.  The GPU analogue of the RoCC load/start/read command sequence
  * (chipyard/ntt-test.c:110-169).  Blocks until c is complete. */
 int tntt_polymul_host(tntt_plan *plan, const void *a_host, const void *b_host, void *c_host, size_t batch);
