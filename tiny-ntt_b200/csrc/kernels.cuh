@@ -173,24 +173,34 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
 #pragma unroll
         for (int a = 0; a < NA; ++a) reduce_top_x<C, kb>(x[a], mod);
     }
+    // twiddles are fetched TG at a time, ahead of their butterflies, so that their latencies overlap
+    constexpr int TG = NG < 4 ? NG : 4;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        Tw<W> t;
-        if constexpr (PRE && B == C::fwd_bhi(PASS) - 1 && NG == 1)
-            t = *pre_t;
-        else if constexpr (LO == C::LOGP && C::R <= MAX_R)  // first pass: same twiddle in every thread -> kernel parameter
-            t = tb.fwd_head[(1 << s) + g];
-        else if constexpr (LO == 0 && SMEM_TW)  // last pass, table staged in shared memory by TMA
-            t = ld_tw_shared(&stab[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
-        else if constexpr (LO == 0)  // last pass: every thread has its own twiddles -> transposed table, coalesced
-            t = ld_tw(&tb.fwd_last[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
-        else                    // middle passes: shared by 2^LO consecutive threads -> broadcast
-            t = ld_tw(&tb.fwd_pyr[(1 << s) + ((tid >> LO) << (C::LOGR - 1 - kb)) + g]);
+    for (int g0 = 0; g0 < NG; g0 += TG) {
+        Tw<W> tw[TG];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
+        for (int gi = 0; gi < TG; ++gi) {
+            const int g = g0 + gi;
+            if constexpr (PRE && B == C::fwd_bhi(PASS) - 1 && NG == 1)
+                tw[gi] = *pre_t;
+            else if constexpr (LO == C::LOGP && C::R <= MAX_R)  // first pass: same twiddle in every thread -> kernel parameter
+                tw[gi] = tb.fwd_head[(1 << s) + g];
+            else if constexpr (LO == 0 && SMEM_TW)  // last pass, table staged in shared memory by TMA
+                tw[gi] = ld_tw_shared(&stab[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
+            else if constexpr (LO == 0)  // last pass: every thread has its own twiddles -> transposed table, coalesced
+                tw[gi] = ld_tw(&tb.fwd_last[((1 << (C::LOGR - 1 - kb)) - 1 + g) * C::P + tid]);
+            else                    // middle passes: shared by 2^LO consecutive threads -> broadcast
+                tw[gi] = ld_tw(&tb.fwd_pyr[(1 << s) + ((tid >> LO) << (C::LOGR - 1 - kb)) + g]);
+        }
 #pragma unroll
-            for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], t, mod);
+        for (int gi = 0; gi < TG; ++gi) {
+            const int g = g0 + gi;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
+#pragma unroll
+                for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], tw[gi], mod);
+            }
         }
     }
     if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1, SMEM_TW, PRE>(x, tid, tb, mod, stab, pre_t);
@@ -257,18 +267,27 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
     } else {
     if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
         reduce_top_x<C, kb>(x, mod);
+    constexpr int TG = NJ < 4 ? NJ : 4;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        Tw<W> t;
-        if constexpr (PRE && B == C::inv_blo(PASS) && NJ == 1) t = *pre_t;
-        else if constexpr (LO == 0 && C::R <= MAX_R) t = dt.head[(1 << B) + j];  // first pass: uniform -> kernel parameter
-        else if constexpr (SMEM_TW && PASS + 1 == C::NPASS)   // last pass, pyr[2^blo ..) staged in shared memory by TMA
-            t = ld_tw_shared(&stab[(1 << B) - (1 << C::inv_blo(PASS)) + (j << LO) + (tid & ((1 << LO) - 1))]);
-        else t = ld_tw(&dt.pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
+    for (int j0 = 0; j0 < NJ; j0 += TG) {
+        Tw<W> tw[TG];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
-            ct_butterfly(x[k0], x[k1], t, mod);
+        for (int ji = 0; ji < TG; ++ji) {
+            const int j = j0 + ji;
+            if constexpr (PRE && B == C::inv_blo(PASS) && NJ == 1) tw[ji] = *pre_t;
+            else if constexpr (LO == 0 && C::R <= MAX_R) tw[ji] = dt.head[(1 << B) + j];  // first pass: uniform -> kernel parameter
+            else if constexpr (SMEM_TW && PASS + 1 == C::NPASS)   // last pass, pyr[2^blo ..) staged in shared memory by TMA
+                tw[ji] = ld_tw_shared(&stab[(1 << B) - (1 << C::inv_blo(PASS)) + (j << LO) + (tid & ((1 << LO) - 1))]);
+            else tw[ji] = ld_tw(&dt.pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
+        }
+#pragma unroll
+        for (int ji = 0; ji < TG; ++ji) {
+            const int j = j0 + ji;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
+                ct_butterfly(x[k0], x[k1], tw[ji], mod);
+            }
         }
     }
     }
@@ -311,18 +330,33 @@ template <class C> TNTT_HD void row_load(typename C::W (&x)[C::R], const typenam
     for (int k = 0; k < C::R; ++k) x[k] = active ? ld_stream(row + (k << C::LOGP) + tid) : (typename C::W)0;
 }
 
-// final multiply (psi^-i N^-1 ...) + canonical reduction + coalesced store
-template <class C>
+// final multiply (psi^-i N^-1 ...) + canonical reduction + coalesced store.
+// TABLE: 1 = per-coefficient table `post` (loaded GROUP entries at a time so that their L2 latencies
+// overlap instead of one exposed load per coefficient), 0 = one uniform factor, -1 = decided at run time.
+template <class C, int TABLE = -1, int GROUP_ = 4>
 TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row, int tid, bool active,
                               const Tw<typename C::W> *post, const Tw<typename C::W> &post_uniform,
                               const Mod<typename C::W> &mod) {
     using W = typename C::W;
+    constexpr int GROUP = GROUP_ < C::R ? GROUP_ : C::R;
+    if (TABLE == 1 || (TABLE == -1 && post)) {
 #pragma unroll
-    for (int k = 0; k < C::R; ++k) {
-        const int e = (k << C::LOGP) + tid;
-        const Tw<W> t = post ? ld_tw(&post[e]) : post_uniform;
-        const W v = csub(shoup_mul(x[k], t.w, t.wp, mod.nq), mod.q);
-        if (active) st_stream(row + e, v);
+        for (int k0 = 0; k0 < C::R; k0 += GROUP) {
+            Tw<W> t[GROUP];
+#pragma unroll
+            for (int j = 0; j < GROUP; ++j) t[j] = ld_tw(&post[((k0 + j) << C::LOGP) + tid]);
+#pragma unroll
+            for (int j = 0; j < GROUP; ++j) {
+                const W v = csub(shoup_mul(x[k0 + j], t[j].w, t[j].wp, mod.nq), mod.q);
+                if (active) st_stream(row + ((k0 + j) << C::LOGP) + tid, v);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) {
+            const W v = csub(shoup_mul(x[k], post_uniform.w, post_uniform.wp, mod.nq), mod.q);
+            if (active) st_stream(row + (k << C::LOGP) + tid, v);
+        }
     }
 }
 
@@ -501,7 +535,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
         }
     }
     dit_all<C, RED, pointwise_out_bound<C, RED>(), (TMA != 0), C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod, tma, stab);
-    row_store_scaled<C>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+    row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -50,6 +50,8 @@ template <int KIND> __global__ void __launch_bounds__(256) k(uint64_t* sink, uin
             if (KIND == 5) x[i] = x[i] * w;                                    // mul.lo.u64
             if (KIND == 6) x[i] = x[i] + w + (x[i] >> 63);                     // 64-bit adds
             if (KIND == 7) { uint32_t lo, hi; unpack(x[i], lo, hi); uint64_t t; asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(lo), "r"(hi)); x[i] = t; }
+            if (KIND == 9) { uint32_t lo, hi; unpack(x[i], lo, hi); asm("mul.hi.u32 %0, %0, %1;" : "+r"(lo) : "r"(hi | 0x80000001u)); x[i] = pack(lo, hi); }
+            if (KIND == 10) { uint32_t lo, hi; unpack(x[i], lo, hi); asm("mad.hi.u32 %0, %0, %1, %1;" : "+r"(lo) : "r"(hi | 0x80000001u)); x[i] = pack(lo, hi); }
             if (KIND == 8) { uint32_t lo, hi; unpack(x[i], lo, hi); asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(lo) : "r"(hi)); x[i] = pack(lo, hi); }
         }
     }
@@ -79,7 +81,7 @@ template <int KIND> double run(const char* name, int ctas_per_sm, double ops_per
 }
 
 int main() {
-    for (int c : {8, 2, 1}) {
+    for (int c : {8}) {
         run<0>("umul64hi (compiler)", c, 1);
         run<1>("mulhi carry-free", c, 1);
         run<2>("T part (6 IMAD)", c, 1);
@@ -89,6 +91,8 @@ int main() {
         run<6>("64-bit add x2", c, 1);
         run<7>("mul.wide.u32", c, 1);
         run<8>("mad.lo.u32", c, 1);
+        run<9>("mul.hi.u32", c, 1);
+        run<10>("mad.hi.u32", c, 1);
     }
     return 0;
 }
