@@ -231,17 +231,16 @@ def run_ours(args):
 
     # parity gate before any timing: row 0/1 = the C++ benchmark's LCG
     # polynomials, whose product checksum is a golden constant of the reference
-    from oracle import ntt_oracle as O
+    from tntt import fixtures
 
     npdt = np.uint32 if wb == 4 else np.uint64
     sdt = np.int32 if wb == 4 else np.int64
-    a[0] = torch.from_numpy(np.array(O.make_poly(tag, 1), dtype=npdt).view(sdt)).cuda()
-    b[0] = torch.from_numpy(np.array(O.make_poly(tag, 2), dtype=npdt).view(sdt)).cuda()
+    a[0] = torch.from_numpy(np.array(fixtures.make_poly(1, n, q), dtype=npdt).view(sdt)).cuda()
+    b[0] = torch.from_numpy(np.array(fixtures.make_poly(2, n, q), dtype=npdt).view(sdt)).cuda()
     tntt.polymul(plan, a, b, out=c)
     torch.cuda.synchronize()
-    golden = {"dilithium": 16424788039373839479, "n1024_24": 15308795525113097448,
-              "n4096_24": 11303505593119465445, "n4096_60": 2710933653778106521}[tag]
-    got = O.checksum(tag, [int(v) for v in c[0].cpu().numpy().view(npdt)])
+    golden = fixtures.REFERENCE_CHECKSUMS[(n, q)]
+    got = fixtures.checksum(c[0].cpu().numpy().view(npdt).tolist(), q)
     if got != golden:
         raise SystemExit(f"parity gate failed: checksum {got} != reference {golden}")
 
@@ -347,6 +346,17 @@ def run_ours(args):
         dt = time.perf_counter() - t
         cpu = {"value": ctx["rows"] / dt, "unit": UNIT, "cores": ctx["cores"], "kind": ctx["kind"],
                "sample": f"{ctx['rows']} polymuls of the same workload, {ctx['name']}, one pass after warm-up"}
+        # the Python golden model (new_reference/cg_ntt.py:78-92, restated in oracle/ntt_oracle.py), one core
+        from oracle import ntt_oracle as O
+
+        pa, pb = [int(v) for v in ctx["a"][0]], [int(v) for v in ctx["b"][0]]
+        t = time.perf_counter()
+        reps = 0
+        while reps < 1 or (time.perf_counter() - t < 2.0 and reps < 50):
+            O.nwc_poly_mult(pa, pb, psi, q)
+            reps += 1
+        cpu["python_reference"] = {"value": reps / (time.perf_counter() - t), "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": f"{reps} polymul(s), oracle/ntt_oracle.py nwc_poly_mult (pure Python)"}
 
     line = {
         "metric": METRIC if tag == "n4096_60" else f"polymuls_per_sec_{tag}", "value": value, "unit": UNIT,

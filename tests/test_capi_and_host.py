@@ -158,3 +158,17 @@ def test_sharded_batches_with_gloo_world_size_2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_benchmark_fixture_helpers_reproduce_the_reference_inputs_and_checksums(golden_all):
+    # tntt.fixtures = make_poly / checksum of the C++ benchmarks, pinned by the golden
+    # vectors that were produced by running the reference itself
+    from tntt import fixtures
+
+    for tag, g in golden_all.items():
+        n, q = g["n"], g["q"]
+        case = g["cases"]["lcg_1_2"]
+        assert fixtures.make_poly(1, n, q) == case["a"], tag
+        assert fixtures.make_poly(2, n, q) == case["b"], tag
+        assert fixtures.checksum(case["c"], q) == fixtures.REFERENCE_CHECKSUMS[(n, q)], tag
+        assert fixtures.REFERENCE_CHECKSUMS[(n, q)] in [int(v) for v in g["cpp_checksums"].values()], tag

@@ -89,8 +89,23 @@ template <typename W> struct TransformTables {
     int reduce_input;   // inputs may be any word: reduce on load
 };
 
+#if defined(TNTT_X_NO_TW_LOADS) && defined(__CUDACC__)
+__constant__ unsigned long long x_fake_tw[2] = {431606828070683274ull, 6905709249130932383ull};   // what-if only
+#endif
 template <typename W> TNTT_HD Tw<W> ld_tw(const Tw<W> *p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(TNTT_X_NO_TW_LOADS)
+    return Tw<W>{(W)x_fake_tw[0], (W)x_fake_tw[1]};
+#elif defined(__CUDA_ARCH__) && defined(TNTT_X_TW_L1HIT)
+    // what-if only: every twiddle load hits the same 512 bytes (always in L1)
+    p = reinterpret_cast<const Tw<W> *>((reinterpret_cast<unsigned long long>(p) & ~0xFFFFFull)) + (threadIdx.x & 31);
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    return Tw<W>{(W)v.x, (W)v.y};
+#elif defined(__CUDA_ARCH__) && defined(TNTT_X_TW_SMEM)
+    // what-if only: every twiddle comes from shared memory (contents are whatever the tile holds)
+    extern __shared__ __align__(16) unsigned char x_smem[];
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(x_smem + ((reinterpret_cast<unsigned long long>(p) & 0x7FF0ull)));
+    return Tw<W>{(W)v.x, (W)v.y};
+#elif defined(__CUDA_ARCH__)
     if constexpr (sizeof(W) == 4) {
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
         return Tw<W>{v.x, v.y};
@@ -368,6 +383,9 @@ constexpr int kTwBufBytes = 65536;   // shared twiddle buffer of the TMA variant
 // ---------------------------------------------------------------------------------------------
 template <class C, int LO_FROM, int LO_TO>
 __device__ __forceinline__ void exchange(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid) {
+#if defined(TNTT_X_NO_EXCHANGE)
+    return;   // what-if only: wrong results
+#endif
     __syncthreads();  // everybody is done reading the tile's previous contents
     tile_write<C, LO_FROM>(x, tile, pl, tid);
     __syncthreads();
@@ -447,7 +465,11 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
         constexpr bool PRE = PASS > 0 && C::inv_lo(PASS) == C::inv_blo(PASS) && !(TMA && PASS + 1 == C::NPASS);
         Tw<typename C::W> t0{};
         if constexpr (PRE) t0 = dit_first_twiddle<C, PASS>(tid, dt);
+#if defined(TNTT_X_NO_EXCHANGE)
+        if constexpr (false) {
+#else
         if constexpr (PASS > 0) {
+#endif
             __syncthreads();  // everybody is done reading the tile (and, for PASS 1, the forward twiddle buffer)
             if constexpr (TMA && PASS == 1) {
                 constexpr int first = 1 << C::inv_blo(C::NPASS - 1);
@@ -505,6 +527,10 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     if constexpr (NA == 1) {
         W x[1][C::R];
         W *stash = tile + C::PPC * C::N + threadIdx.x;
+#if defined(TNTT_X_PREFETCH_B)
+        // b's row is needed one forward transform from now: pull it into L2 (one 128-byte line per thread)
+        if (threadIdx.x * 16 < C::N) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + off + threadIdx.x * 16));
+#endif
         row_load<C>(x[0], a + off, tid, active);
         forward_all<C, 1, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, true);
 #pragma unroll

@@ -176,6 +176,18 @@ TNTT_HD uint64_t shoup_lazy(uint64_t y, uint64_t w, uint64_t wp, const Mod<uint6
     unpack64(m.nq, n0, n1);
     uint64_t acc;   // low 64 bits of y*w + h*nq: one IMAD.WIDE chain plus four IMAD.LO into the high word
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(y0), "r"(w0));
+#if defined(TNTT_X_TPART_REORDER)
+    // everything that does not depend on the quotient first: only 3 multiplies follow h instead of 5
+    unpack64(acc, lo, hi);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y0), "r"(w1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y1), "r"(w0));
+    acc = pack64(lo, hi);
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
+    unpack64(acc, lo, hi);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h0), "r"(n1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(n0));
+    return pack64(lo, hi);
+#endif
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
     unpack64(acc, lo, hi);
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h0), "r"(n1));

@@ -5,6 +5,7 @@ The reference-compatible entry points live one level up, in ``cg_ntt.py`` and
 new_reference/ modules); this package holds the binding, the plan cache and the
 batched tensor API they are built on.
 """
+from . import fixtures  # noqa: F401
 from ._lib import LIB_PATH, SYMBOLS, TnttError, lib  # noqa: F401
 from .ops import (as_tensor, bit_reverse, butterfly_lanes, cg_stage, forward, inverse, microbench, pointwise,  # noqa: F401
                   polymul, polymul_host, reduce, scale)
@@ -15,5 +16,5 @@ from .shard import shard_range, shard_rows  # noqa: F401
 __all__ = [
     "Plan", "get_plan", "clear_plan_cache", "forward", "inverse", "pointwise", "polymul", "polymul_host", "cg_stage",
     "bit_reverse", "scale", "reduce", "butterfly_lanes", "microbench", "shard_range", "shard_rows", "TnttError", "lib",
-    "RnsContext", "find_psi",
+    "RnsContext", "find_psi", "fixtures",
 ]
