@@ -66,6 +66,12 @@ typedef struct tntt_plan_info {
     int lazy_reduce;           /* 1: kernels reduce lazily before every pass (q close to 2^60) */
     int default_variant;       /* index into tntt_variant_* used by tntt_polymul */
     int device;
+    /* batch-size dispatch of tntt_polymul (-1 = none): batch <= cluster_batch_max -> cluster_variant (one row
+     * per thread-block cluster, exchanges through distributed shared memory), else batch <= small_batch_max ->
+     * small_variant (one CTA per SM, all registers), else default_variant.  tntt_plan_set_default_variant
+     * switches the dispatch off. */
+    int cluster_variant, cluster_batch_max;
+    int small_variant, small_batch_max;
 } tntt_plan_info;
 
 /* Ring parameters N, Q of new_reference/cg_ntt.py:5-6 plus the root the caller passes to

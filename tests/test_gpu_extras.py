@@ -72,3 +72,68 @@ def test_tma_variant_agrees_and_is_listed():
         for _ in range(3):   # back-to-back launches reuse the mbarrier phase logic from scratch each time
             got = tntt.polymul(plan, da, db, variant=v).cpu().numpy().view(np.uint64)
             assert (got == want).all()
+
+
+def test_refs_twins_match_the_reference_outputs():
+    # tests/golden/golden_refs.json was produced by the reference's own test/refs modules
+    # (tests/golden/make_golden_refs.py); inputs are unreduced / negative on purpose
+    import json
+
+    from refs import ntt_forward_reference, ntt_inverse_reference
+    from refs.ntt_forward_reference import bit_reverse_order
+
+    with open(os.path.join(ROOT, "tests", "golden", "golden_refs.json")) as fh:
+        cases = json.load(fh)
+    for c in cases:
+        n, q, psi = c["n"], c["q"], c["psi"]
+        assert ntt_forward_reference(c["x"], n, q, psi) == c["forward"], (n, q)
+        assert ntt_inverse_reference(c["x"], n, q, psi) == c["inverse"], (n, q)
+        assert ntt_inverse_reference(c["forward"], n, q, psi) == [v % q for v in c["x"]]
+    with pytest.raises(ValueError, match="Input must have 256 coefficients, got 3"):
+        ntt_forward_reference([1, 2, 3], 256, 8380417, 1239911)
+    with pytest.raises(ValueError, match="Input must have 4096 coefficients, got 2"):
+        ntt_inverse_reference([1, 2])                      # module defaults: NTT_N = 4096
+    assert bit_reverse_order(8) == [0, 4, 2, 6, 1, 5, 3, 7]
+
+
+@pytest.mark.parametrize("tag", ["n4096_60", "n4096_24"])
+def test_batch_size_dispatch_cluster_and_small_shapes(tag):
+    # tntt_polymul picks the cluster kernel (one row per 4-CTA cluster, DSMEM exchanges) for tiny batches and
+    # the one-CTA-per-SM shape up to one row per SM; every choice must give the oracle's bits
+    import tntt
+
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    tntt.clear_plan_cache()
+    plan = tntt.get_plan(n, q, psi, True)
+    names = dict((v, d.split()[0]) for v, d in plan.variants())
+    assert any(nm.endswith("_c4") for nm in names.values())          # the cluster kernel exists for both word sizes
+    if tag == "n4096_60":
+        assert plan.cluster_variant >= 0 and names[plan.cluster_variant].endswith("_c4")
+        assert plan.cluster_batch_max == torch.cuda.get_device_properties(0).multi_processor_count // 4
+        assert plan.small_variant >= 0 and plan.small_batch_max >= plan.cluster_batch_max
+    else:
+        assert plan.cluster_variant == -1      # 32-bit rows: dispatch keeps the one-CTA kernel (measured no gain)
+    co = COracle()
+    npdt = np.uint32 if plan.word_bytes == 4 else np.uint64
+    sdt = np.int32 if plan.word_bytes == 4 else np.int64
+    rng = np.random.default_rng(11)
+    edges = sorted({1, 2, plan.cluster_batch_max, plan.cluster_batch_max + 1, max(plan.small_batch_max, 1),
+                    max(plan.small_batch_max, 1) + 1})
+    for rows in edges:
+        a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+        b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+        a[0], b[0] = q - 1, q - 1
+        ta = torch.from_numpy(a.astype(npdt).view(sdt)).cuda()
+        tb = torch.from_numpy(b.astype(npdt).view(sdt)).cuda()
+        got = tntt.polymul(plan, ta, tb).cpu().numpy().view(npdt).astype(np.uint64)
+        assert (got == co.nwc_poly_mult(a, b, psi, q, threads=8)).all(), rows
+        # in place on the first operand
+        tntt.polymul(plan, ta, tb, out=ta)
+        assert (ta.cpu().numpy().view(npdt).astype(np.uint64) == got).all(), rows
+    # an explicit default switches the dispatch off
+    plan.set_default_variant(plan.default_variant)
+    info = tntt._lib.PlanInfo()
+    tntt.lib().tntt_plan_info_get(plan._h, __import__("ctypes").byref(info))
+    assert info.cluster_variant == -1 and info.small_variant == -1
+    tntt.clear_plan_cache()

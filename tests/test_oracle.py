@@ -155,3 +155,16 @@ def test_reference_cpp_build_agrees_with_oracle(tag, coracle):
     want = coracle.nwc_poly_mult(a, b, lib.psi, lib.q, threads=2)
     assert (got == want).all()
     assert lib.checksum(lib.polymul(lib.make_poly(1), lib.make_poly(2))) == SURVEY_CHECKSUMS[tag][1]
+
+
+def test_oracle_matches_the_reference_refs_twins():
+    # test/refs/ntt_forward_reference.py / ntt_inverse_reference.py: cg_ntt over psi^2
+    # with inputs reduced first; vectors generated by the reference (tests/golden/make_golden_refs.py)
+    with open(os.path.join(GOLDEN_DIR, "golden_refs.json")) as fh:
+        cases = json.load(fh)
+    assert len(cases) >= 4
+    for c in cases:
+        n, q, omega = c["n"], c["q"], pow(c["psi"], 2, c["q"])
+        x = [v % q for v in c["x"]]
+        assert O.cg_ntt(x, omega, q) == c["forward"]
+        assert O.cg_intt(x, omega, q) == c["inverse"]

@@ -151,8 +151,38 @@ int choose_default_variant(const tntt_plan *p) {
         for (size_t i = 0; i < vs.size(); ++i)
             if (!strcmp(vs[i].name, name) && tntt_variant_matches(p, (int)i)) return (int)i;
     for (size_t i = 0; i < vs.size(); ++i)
-        if (tntt_variant_matches(p, (int)i)) return (int)i;
+        if (!vs[i].cluster && tntt_variant_matches(p, (int)i)) return (int)i;
     return -1;
+}
+
+int find_variant(const tntt_plan *p, const char *name) {
+    const std::vector<PolymulVariant> &vs = all_variants();
+    for (size_t i = 0; i < vs.size(); ++i)
+        if (!strcmp(vs[i].name, name) && tntt_variant_matches(p, (int)i)) return (int)i;
+    return -1;
+}
+// Small batches (measured on B200, profiles/r01_small_batch.jsonl): with fewer rows than SMs a row's latency is
+// what counts.  Up to SMs/4 rows every row gets a cluster of 4 SMs; up to one row per SM the one-CTA-per-SM
+// shape (all 64K registers, no stash tile) beats the three-CTAs-per-SM throughput shape.
+void choose_small_batch_variants(tntt_plan *p) {
+    tntt_plan_info &I = p->info;
+    I.cluster_variant = I.small_variant = -1;
+    I.cluster_batch_max = I.small_batch_max = 0;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, I.device) != cudaSuccess || sms <= 0) return;
+    const std::vector<PolymulVariant> &vs = all_variants();
+    for (size_t i = 0; i < vs.size(); ++i)
+        // 64-bit words only: the 32-bit rows are short enough that the cluster barriers eat the gain (measured)
+        if (vs[i].cluster > 0 && vs[i].word_bytes == 8 && tntt_variant_matches(p, (int)i)) {
+            I.cluster_variant = (int)i;
+            I.cluster_batch_max = sms / vs[i].cluster;
+            break;
+        }
+    static const char *small[] = {"u64_n12_r3_p1_a1_red1_b1_s0_t0"};
+    for (const char *name : small) {
+        const int v = find_variant(p, name);
+        if (v >= 0) { I.small_variant = v; I.small_batch_max = sms; break; }
+    }
 }
 
 int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t root, int root_is_psi) {
@@ -225,6 +255,7 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
         }
     I.default_variant = choose_default_variant(p);
     I.fused = I.default_variant >= 0 ? 1 : 0;
+    choose_small_batch_variants(p);
     CUDA_TRY(cudaDeviceSynchronize());
     *out = p;
     return TNTT_OK;
@@ -438,6 +469,8 @@ int tntt_variant_matches(const tntt_plan *p, int variant) {
 int tntt_plan_set_default_variant(tntt_plan *p, int variant) {
     if (!tntt_variant_matches(p, variant)) return fail(TNTT_BAD_ARG, "variant %d does not match the plan", variant);
     p->info.default_variant = variant;
+    p->info.cluster_variant = p->info.small_variant = -1;   // an explicit choice switches the batch-size dispatch off
+    p->info.cluster_batch_max = p->info.small_batch_max = 0;
     return TNTT_OK;
 }
 
@@ -459,7 +492,12 @@ int tntt_polymul(const tntt_plan *p, const void *a, const void *b, void *c, size
     if (!p->info.has_psi) return fail(TNTT_BAD_ARG, "polymul needs a plan created from psi");
     if (batch == 0) return TNTT_OK;
     if (!c || ((uintptr_t)c & 15)) return fail(TNTT_BAD_ARG, "c must be a 16-byte aligned device pointer");
-    if (p->info.default_variant >= 0) return tntt_polymul_variant(p, p->info.default_variant, a, b, c, batch, stream);
+    if (p->info.default_variant >= 0) {
+        int v = p->info.default_variant;
+        if (p->info.cluster_variant >= 0 && batch <= (size_t)p->info.cluster_batch_max) v = p->info.cluster_variant;
+        else if (p->info.small_variant >= 0 && batch <= (size_t)p->info.small_batch_max) v = p->info.small_variant;
+        return tntt_polymul_variant(p, v, a, b, c, batch, stream);
+    }
     DeviceSetter ds(p->info.device);
     return generic_polymul(p, a, b, c, batch, (cudaStream_t)stream);
 }

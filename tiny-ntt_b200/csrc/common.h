@@ -19,6 +19,7 @@ struct PolymulVariant {
                           cudaStream_t stream);
     cudaError_t (*prepare)();                                   // opt in to > 48 KB dynamic smem
     cudaError_t (*attributes)(cudaFuncAttributes *attr, int *blocks_per_sm);
+    int cluster = 0;   // > 0: one row per thread-block cluster of this many CTAs (polymul_cluster_kernel)
 };
 // one instantiation of the standalone natural-order transform kernel
 struct TransformVariant {

@@ -175,7 +175,8 @@ template <typename W> TNTT_HD Tw<W> ld_tw_shared(const Tw<W> *p) {
 // STAB: non-null = shared-memory copy of fwd_last (only read when SMEM_TW)
 // PRE: the twiddle of the pass's first stage was loaded before the tile exchange (pre_t), so its
 // latency overlaps the barriers instead of following them
-template <class C, int PASS, int NA, bool RED, int B, bool SMEM_TW = false, bool PRE = false>
+// ALLPRE: all R-1 twiddles of the pass were loaded beforehand into pre_t[slot] (fwd_load_pass_twiddles)
+template <class C, int PASS, int NA, bool RED, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                        const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr,
                        const Tw<typename C::W> *pre_t = nullptr) {
@@ -196,7 +197,9 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
 #pragma unroll
         for (int gi = 0; gi < TG; ++gi) {
             const int g = g0 + gi;
-            if constexpr (PRE && B == C::fwd_bhi(PASS) - 1 && NG == 1)
+            if constexpr (ALLPRE)
+                tw[gi] = pre_t[(1 << (C::LOGR - 1 - kb)) - 1 + g];
+            else if constexpr (PRE && B == C::fwd_bhi(PASS) - 1 && NG == 1)
                 tw[gi] = *pre_t;
             else if constexpr (LO == C::LOGP && C::R <= MAX_R)  // first pass: same twiddle in every thread -> kernel parameter
                 tw[gi] = tb.fwd_head[(1 << s) + g];
@@ -218,7 +221,24 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
             }
         }
     }
-    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1, SMEM_TW, PRE>(x, tid, tb, mod, stab, pre_t);
+    if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1, SMEM_TW, PRE, ALLPRE>(x, tid, tb, mod, stab, pre_t);
+}
+// all twiddles of forward pass PASS (a pass that runs all log2 R stages), slot = 2^(LOGR-1-kb) - 1 + g
+template <class C, int PASS> TNTT_HD void fwd_load_pass_twiddles(Tw<typename C::W> (&t)[C::R - 1], int tid,
+                                                                 const PolymulTables<typename C::W> &tb) {
+    constexpr int LO = C::fwd_lo(PASS);
+    static_assert(C::fwd_bhi(PASS) - LO == C::LOGR, "full passes only");
+#pragma unroll
+    for (int kb = C::LOGR - 1; kb >= 0; --kb) {
+        const int s = C::LOGN - 1 - (LO + kb);
+#pragma unroll
+        for (int g = 0; g < (C::R >> (kb + 1)); ++g) {
+            const int slot = (1 << (C::LOGR - 1 - kb)) - 1 + g;
+            if constexpr (LO == C::LOGP && C::R <= MAX_R) t[slot] = tb.fwd_head[(1 << s) + g];
+            else if constexpr (LO == 0) t[slot] = ld_tw(&tb.fwd_last[slot * C::P + tid]);
+            else t[slot] = ld_tw(&tb.fwd_pyr[(1 << s) + ((tid >> LO) << (C::LOGR - 1 - kb)) + g]);
+        }
+    }
 }
 // the single twiddle of the first stage of forward pass PASS (valid when that pass runs all log2 R stages)
 template <class C, int PASS> TNTT_HD Tw<typename C::W> fwd_first_twiddle(int tid, const PolymulTables<typename C::W> &tb) {
@@ -249,11 +269,11 @@ template <class C> TNTT_HD void prefetch_post(int tid, const Tw<typename C::W> *
     for (int k = 0; k < C::R; ++k) prefetch_l1(&post[(k << C::LOGP) + tid]);
 }
 
-template <class C, int PASS, int NA, bool RED, bool SMEM_TW = false, bool PRE = false>
+template <class C, int PASS, int NA, bool RED, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void fwd_pass(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                       const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr,
                       const Tw<typename C::W> *pre_t = nullptr) {
-    fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1, SMEM_TW, PRE>(x, tid, tb, mod, stab, pre_t);
+    fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1, SMEM_TW, PRE, ALLPRE>(x, tid, tb, mod, stab, pre_t);
 }
 // bound (units of 2^(BITS-4)) of the spectrum a forward transform of canonical input leaves in registers
 template <class C, bool RED> TNTT_CX int fwd_out_bound() {
@@ -269,7 +289,7 @@ template <class C, bool RED> TNTT_CX int pointwise_out_bound() {
 // cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
 // ---------------------------------------------------------------------------------------------
 // IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
-template <class C, int PASS, bool RED, int IN_BND, int B, bool SMEM_TW = false, bool PRE = false>
+template <class C, int PASS, bool RED, int IN_BND, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
                        const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
     using W = typename C::W;
@@ -289,7 +309,8 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
 #pragma unroll
         for (int ji = 0; ji < TG; ++ji) {
             const int j = j0 + ji;
-            if constexpr (PRE && B == C::inv_blo(PASS) && NJ == 1) tw[ji] = *pre_t;
+            if constexpr (ALLPRE) tw[ji] = pre_t[(1 << kb) - 1 + j];
+            else if constexpr (PRE && B == C::inv_blo(PASS) && NJ == 1) tw[ji] = *pre_t;
             else if constexpr (LO == 0 && C::R <= MAX_R) tw[ji] = dt.head[(1 << B) + j];  // first pass: uniform -> kernel parameter
             else if constexpr (SMEM_TW && PASS + 1 == C::NPASS)   // last pass, pyr[2^blo ..) staged in shared memory by TMA
                 tw[ji] = ld_tw_shared(&stab[(1 << B) - (1 << C::inv_blo(PASS)) + (j << LO) + (tid & ((1 << LO) - 1))]);
@@ -306,12 +327,28 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
         }
     }
     }
-    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1, SMEM_TW, PRE>(x, tid, dt, mod, stab, pre_t);
+    if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1, SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
 }
-template <class C, int PASS, bool RED, int IN_BND, bool SMEM_TW = false, bool PRE = false>
+template <class C, int PASS, bool RED, int IN_BND, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
                       const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
-    dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS), SMEM_TW, PRE>(x, tid, dt, mod, stab, pre_t);
+    dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS), SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
+}
+// all twiddles of inverse pass PASS (full passes only), slot = 2^kb - 1 + j; slot 0 of pass 0 is the trivial twiddle 1
+template <class C, int PASS> TNTT_HD void dit_load_pass_twiddles(Tw<typename C::W> (&t)[C::R - 1], int tid,
+                                                                 const DitTables<typename C::W> &dt) {
+    constexpr int LO = C::inv_lo(PASS);
+    static_assert(C::inv_bhi(PASS) - C::inv_blo(PASS) == C::LOGR && LO == C::inv_blo(PASS), "full passes only");
+#pragma unroll
+    for (int kb = 0; kb < C::LOGR; ++kb) {
+        const int B = LO + kb;
+#pragma unroll
+        for (int j = 0; j < (1 << kb); ++j) {
+            const int slot = (1 << kb) - 1 + j;
+            if constexpr (LO == 0 && C::R <= MAX_R) t[slot] = dt.head[(1 << B) + j];
+            else t[slot] = ld_tw(&dt.pyr[(1 << B) + (j << LO) + (tid & ((1 << LO) - 1))]);
+        }
+    }
 }
 // the single twiddle of the first stage of inverse pass PASS (valid when its register field starts at that bit)
 template <class C, int PASS> TNTT_HD Tw<typename C::W> dit_first_twiddle(int tid, const DitTables<typename C::W> &dt) {
@@ -509,6 +546,9 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
     const bool active = poly < batch;
     const size_t off = active ? poly * C::N : 0;
+#if defined(TNTT_X_EMPTY_KERNEL)
+    if (batch) return;   // what-if only: launch overhead calibration
+#endif
 
     // shared memory: [NA tiles][stash tile][64 KB twiddle buffer][mbarrier]
     TmaStage tma_s;
@@ -562,6 +602,116 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     }
     dit_all<C, RED, pointwise_out_bound<C, RED>(), (TMA != 0), C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod, tma, stab);
     row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small batches: ONE polynomial pair per thread-block CLUSTER (N = 4096)
+//
+// With fewer rows than SMs the one-CTA-per-row kernel leaves most of the chip idle and a row's latency is
+// that of 8 warps working through ~6000 instructions each.  Here the P = N/R threads of a row are spread
+// over CS CTAs (CS SMs) of a cluster.  Between passes the coefficients are regrouped through DISTRIBUTED
+// shared memory: every thread stores each of its R values straight into the shared memory of the CTA
+// whose thread needs it next (mapa + st.shared::cluster), into that thread's private slot [k][thread], so
+// the read side is local, contiguous and conflict-free.  Two tile buffers alternate, which makes one
+// cluster barrier per exchange sufficient (a buffer is rewritten two exchanges later, after every reader
+// has passed the barrier in between).  The twiddles of the next pass are fetched into registers BEFORE the
+// barrier, so their L2 latency overlaps the exchange instead of following it.
+//   rtl/ntt_coeff_banks.v (ping-pong banks) + rtl/ntt_bank_switch.v -> the two DSMEM tile buffers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <typename W> __device__ __forceinline__ void st_cluster(unsigned local_saddr, unsigned rank, W v) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_saddr), "r"(rank));
+    if constexpr (sizeof(W) == 4) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+    else asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
+}
+// registers (field at LO_FROM) -> the slots of their next owners (field at LO_TO), cluster barrier, local read
+template <class C, int CS, int LO_FROM, int LO_TO>
+__device__ __forceinline__ void cluster_exchange(typename C::W (&x)[C::R], typename C::W *buf, int gtid) {
+    using W = typename C::W;
+    constexpr int T = C::P / CS;
+    const unsigned base = (unsigned)__cvta_generic_to_shared(buf);
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) {
+        const int E = C::template elem<LO_FROM>(gtid, k);
+        const int g2 = ((E >> (LO_TO + C::LOGR)) << LO_TO) | (E & ((1 << LO_TO) - 1));   // next owner (row-wide thread id)
+        const int k2 = (E >> LO_TO) & (C::R - 1);                                        // ... and its register
+        st_cluster<W>(base + (unsigned)((k2 * T + (g2 % T)) * sizeof(W)), (unsigned)(g2 / T), x[k]);
+    }
+    cluster_barrier();
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) x[k] = buf[k * T + (gtid % T)];
+}
+
+template <class C, int CS, bool RED, int XI, int PASS = 1>
+__device__ __forceinline__ void cluster_forward_rest(typename C::W (&x)[1][C::R], typename C::W *tiles, int gtid,
+                                                     const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod) {
+    if constexpr (PASS < C::NPASS) {
+        Tw<typename C::W> tw[C::R - 1];
+        fwd_load_pass_twiddles<C, PASS>(tw, gtid, tb);
+        cluster_exchange<C, CS, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[0], tiles + ((XI + PASS) & 1) * (C::N / CS), gtid);
+        fwd_pass<C, PASS, 1, RED, false, false, true>(x, gtid, tb, mod, nullptr, tw);
+        cluster_forward_rest<C, CS, RED, XI, PASS + 1>(x, tiles, gtid, tb, mod);
+    }
+}
+template <class C, int CS, bool RED, int IN_BND, int XI, int PASS = 1>
+__device__ __forceinline__ void cluster_inverse_rest(typename C::W (&x)[C::R], typename C::W *tiles, int gtid,
+                                                     const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
+    if constexpr (PASS < C::NPASS) {
+        Tw<typename C::W> tw[C::R - 1];
+        dit_load_pass_twiddles<C, PASS>(tw, gtid, dt);
+        cluster_exchange<C, CS, C::inv_lo(PASS - 1), C::inv_lo(PASS)>(x, tiles + ((XI + PASS) & 1) * (C::N / CS), gtid);
+        dit_pass<C, PASS, RED, IN_BND, false, false, true>(x, gtid, dt, mod, nullptr, tw);
+        cluster_inverse_rest<C, CS, RED, IN_BND, XI, PASS + 1>(x, tiles, gtid, dt, mod);
+    }
+}
+
+// launched with a cluster dimension of CS (cudaLaunchKernelEx); grid = rows * CS CTAs of P / CS threads
+template <class C, int CS, bool RED>
+__global__ void __launch_bounds__(C::P / CS, 1)
+polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
+                       size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
+                       const __grid_constant__ Mod<typename C::W> mod) {
+    using W = typename C::W;
+    static_assert(C::PPC == 1 && C::LOGN % C::LOGR == 0 && C::P % CS == 0, "cluster kernel: full passes, one row per cluster");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tiles = reinterpret_cast<W *>(smem_raw);                 // two buffers of N / CS words
+    const int gtid = (int)cluster_ctarank() * (C::P / CS) + (int)threadIdx.x;
+    const size_t row = blockIdx.x / CS;
+    const bool active = row < batch;
+    const size_t off = active ? row * C::N : 0;
+    constexpr int NX = C::NPASS - 1;                            // exchanges per transform
+#if defined(TNTT_X_EMPTY_KERNEL)
+    if (batch) return;   // what-if only: launch overhead calibration
+#endif
+
+    W x[1][C::R], fa[C::R];
+    prefetch_post<C>(gtid, tb.post);
+    row_load<C>(x[0], a + off, gtid, active);
+    row_load<C>(fa, b + off, gtid, active);                      // b's latency overlaps a's transform
+    fwd_pass<C, 0, 1, RED>(x, gtid, tb, mod);
+    cluster_forward_rest<C, CS, RED, 0>(x, tiles, gtid, tb, mod);
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) { const W t = x[0][k]; x[0][k] = fa[k]; fa[k] = t; }
+    fwd_pass<C, 0, 1, RED>(x, gtid, tb, mod);
+    cluster_forward_rest<C, CS, RED, NX>(x, tiles, gtid, tb, mod);
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) {
+        W u = fa[k];
+        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
+        fa[k] = mont_mul(u, x[0][k], mod);
+    }
+    dit_pass<C, 0, RED, pointwise_out_bound<C, RED>()>(fa, gtid, tb.inv, mod);
+    cluster_inverse_rest<C, CS, RED, pointwise_out_bound<C, RED>(), 2 * NX>(fa, tiles, gtid, tb.inv, mod);
+    row_store_scaled<C, 1>(fa, c + off, gtid, active, tb.post, Tw<W>{0, 0}, mod);
+    // no trailing barrier: the last remote store into this CTA's shared memory precedes the last exchange's barrier
 }
 
 // ---------------------------------------------------------------------------------------------

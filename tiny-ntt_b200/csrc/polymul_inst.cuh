@@ -28,6 +28,47 @@ template <class C, int NA, bool RED, int MINB, int STASH = 0, int TMA = 0> struc
     }
 };
 
+// one row per cluster of CS CTAs (small batches); launched with a cluster-dimension attribute
+template <class C, int CS, bool RED> struct PolymulClusterInst {
+    using W = typename C::W;
+    static constexpr size_t SMEM = 2 * (size_t)(C::N / CS) * sizeof(W);
+    static cudaError_t launch(const void *a, const void *b, void *c, size_t batch, const void *tables, const void *mod,
+                              cudaStream_t stream) {
+        if (batch == 0) return cudaSuccess;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(batch * CS));
+        cfg.blockDim = dim3(C::P / CS);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CS;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, polymul_cluster_kernel<C, CS, RED>, static_cast<const W *>(a), static_cast<const W *>(b),
+                                  static_cast<W *>(c), batch, *static_cast<const PolymulTables<W> *>(tables),
+                                  *static_cast<const Mod<W> *>(mod));
+    }
+    static cudaError_t prepare() {
+        return cudaFuncSetAttribute(polymul_cluster_kernel<C, CS, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    }
+    static cudaError_t attributes(cudaFuncAttributes *attr, int *blocks_per_sm) {
+        cudaError_t e = cudaFuncGetAttributes(attr, polymul_cluster_kernel<C, CS, RED>);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, polymul_cluster_kernel<C, CS, RED>, C::P / CS, SMEM);
+    }
+};
+#define TNTT_POLYMUL_CLUSTER(WT, WB, LN, LR, CS, RED)                                                                 \
+    PolymulVariant {                                                                                                  \
+        "u" #WB "_n" #LN "_r" #LR "_p1_a1_red" #RED "_c" #CS, WB / 8, LN, LR, 1, 1, RED, Cfg<WT, LN, LR, 1>::P / CS, 1, \
+            PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::SMEM,                                              \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::launch,                                           \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::prepare,                                          \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::attributes, CS                                    \
+    }
+
 #define TNTT_POLYMUL_VARIANT(WT, WB, LN, LR, PPC, NA, RED, MINB) TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, 0, 0)
 #define TNTT_POLYMUL_VARIANT_S(WT, WB, LN, LR, PPC, NA, RED, MINB, ST) TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, ST, 0)
 #define TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, ST, TM)                                              \

@@ -18,6 +18,8 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 12, 4, 1, 2, 0, 4),
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 12, 5, 2, 1, 0, 2),
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 12, 3, 1, 2, 0, 2),
+    // small batches: one row per cluster of 4 CTAs, exchanges through distributed shared memory
+    TNTT_POLYMUL_CLUSTER(uint32_t, 32, 12, 3, 4, 0),
 };
 const PolymulVariant *polymul_variants_u32(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));

@@ -20,6 +20,9 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 1, 1, 2, 0, 1),
     TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 1, 1, 1, 1, 1),
     TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 2, 1, 1, 0, 1),
+    // small batches: one row per cluster of 4 CTAs, exchanges through distributed shared memory
+    TNTT_POLYMUL_CLUSTER(uint64_t, 64, 12, 3, 4, 1),
+    TNTT_POLYMUL_CLUSTER(uint64_t, 64, 12, 3, 4, 0),
 };
 const PolymulVariant *polymul_variants_u64(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
