@@ -188,6 +188,31 @@ TNTT_HD uint64_t shoup_lazy(uint64_t y, uint64_t w, uint64_t wp, const Mod<uint6
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h1), "r"(n0));
     return pack64(lo, hi);
 #endif
+#if defined(TNTT_X_SOLINAS_CROSS)
+    // experiment, q = 2^60 - 2^14 + 1 only: nq = 2^64 - q has n0 = 2^14 - 1, n1 = -2^28 (mod 2^32), so the two
+    // cross products h0*n1 + h1*n0 are (h1 << 14) - h1 - (h0 << 28): ALU work instead of multiplier work
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
+    unpack64(acc, lo, hi);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y0), "r"(w1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y1), "r"(w0));
+    {
+        uint32_t t1, t2;
+#if TNTT_X_SOLINAS_CROSS == 1
+        asm("shl.b32 %0, %1, 14;" : "=r"(t1) : "r"(h1));
+        asm("shl.b32 %0, %1, 28;" : "=r"(t2) : "r"(h0));
+        asm("sub.u32 %0, %0, %1;" : "+r"(t1) : "r"(h1));
+        asm("{\n\t.reg .u32 z;\n\tsub.u32 z, %1, %2;\n\tadd.u32 %0, %0, z;\n\t}" : "+r"(hi) : "r"(t1), "r"(t2));
+#elif TNTT_X_SOLINAS_CROSS == 2
+        // funnel shifts cannot be expressed as IMAD: shf.l.wrap(lo = zero, hi = x, s) == x << s
+        const uint32_t z = (uint32_t)m.zero;
+        asm("shf.l.wrap.b32 %0, %1, %2, 14;" : "=r"(t1) : "r"(z), "r"(h1));
+        asm("shf.l.wrap.b32 %0, %1, %2, 28;" : "=r"(t2) : "r"(z), "r"(h0));
+        hi = hi + t1 - h1;          // three-input adds stay on the ALU
+        hi = hi - t2 + z;
+#endif
+    }
+    return pack64(lo, hi);
+#endif
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(h0), "r"(n0));
     unpack64(acc, lo, hi);
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(h0), "r"(n1));
