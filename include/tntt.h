@@ -72,6 +72,7 @@ typedef struct tntt_plan_info {
      * switches the dispatch off. */
     int cluster_variant, cluster_batch_max;
     int small_variant, small_batch_max;
+    int spectrum;              /* 1: tntt_spectrum_forward / _inverse / tntt_polymul_spectrum are available */
 } tntt_plan_info;
 
 /* Ring parameters N, Q of new_reference/cg_ntt.py:5-6 plus the root the caller passes to
@@ -132,6 +133,22 @@ int tntt_reduce(const tntt_plan *plan, const void *in, void *out, size_t batch, 
  * butterfly / butterfly_batch of new_reference/cg_ntt_8butterfly.py:8-27; rtl/ntt_butterfly.v:43-72. */
 int tntt_butterfly_batch(int device, uint64_t q, const uint64_t *a, const uint64_t *b, const uint64_t *w, uint64_t *out_a,
                          uint64_t *out_b, size_t count, void *cuda_stream);
+
+/* Operands kept in the transform domain (one forward transform per operand, reused across many products: the
+ * RLWE use the reference targets, reports/final-report.tex:571-610).  A "spectrum" row holds ntt(twist(a))
+ * (new_reference/cg_ntt.py:82-87; forward_ntt_bench, software_benchmark/benchmark_ntt.cpp:207-211) as canonical
+ * values in a plan-specific order: the order in which the fused kernel holds the transform in registers, so that
+ * neither producer nor consumer pays a bit reversal or a twist pass.  Treat the order as opaque; it is a fixed
+ * permutation of the natural-order transform, so element-wise work (tntt_pointwise, additions) applies directly.
+ *   tntt_spectrum_forward : coefficients -> spectrum
+ *   tntt_spectrum_inverse : spectrum -> coefficients, i.e. untwist(cg_intt(.)) (cg_ntt.py:90-92)
+ *   tntt_polymul_spectrum : c = a * b in Z_q[x]/(x^n+1) with b given as spectrum; b_rows = batch (one per row) or
+ *                           1 (one spectrum shared by the whole batch).  Bit-identical to tntt_polymul.
+ * Available when tntt_plan_info.spectrum is 1 (plans created from psi with n in {256, 1024, 4096}). */
+int tntt_spectrum_forward(const tntt_plan *plan, const void *in, void *out, size_t batch, void *cuda_stream);
+int tntt_spectrum_inverse(const tntt_plan *plan, const void *in, void *out, size_t batch, void *cuda_stream);
+int tntt_polymul_spectrum(const tntt_plan *plan, const void *a, const void *b_spectrum, void *c, size_t batch,
+                          size_t b_rows, void *cuda_stream);
 
 /* Kernel variants of the fused polymul (tile shape, operands side by side, ...), for benchmarking. */
 int tntt_variant_count(void);

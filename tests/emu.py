@@ -24,6 +24,7 @@ def lib():
         L.emu_polymul.argtypes = [C.c_int] * 6 + [C.c_void_p] * 3 + [C.c_size_t, C.c_uint64, C.c_uint64]
         L.emu_transform.argtypes = [C.c_int] * 5 + [C.c_void_p] * 2 + [C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.emu_slot.argtypes = [C.c_int] * 7
+        L.emu_spectrum.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_size_t, C.c_uint64, C.c_uint64, C.c_int]
         for name, t in (("emu_shoup64", C.c_uint64), ("emu_shoup_lazy64", C.c_uint64), ("emu_mont64", C.c_uint64), ("emu_barrett64", C.c_uint64),
                         ("emu_csub_top64", C.c_uint64), ("emu_shoup32", C.c_uint32), ("emu_mont32", C.c_uint32),
                         ("emu_barrett32", C.c_uint32)):
@@ -47,6 +48,18 @@ def polymul(wb, logn, logr, ppc, na, red, a, b, q, psi):
     if rc:
         raise RuntimeError(f"emu_polymul rc={rc}")
     return c
+
+
+def spectrum(wb, logn, logr, ppc, red, a, b, q, psi, mode):
+    """mode 0: inverse(forward(a)); 1: polymul_spectrum(a, forward(b)); 2: same, b[0]'s spectrum shared; 3: forward(a)"""
+    dt = np.uint32 if wb == 4 else np.uint64
+    a = np.ascontiguousarray(a, dtype=dt)
+    b = np.ascontiguousarray(b, dtype=dt)
+    out = np.zeros_like(a)
+    rc = lib().emu_spectrum(wb, logn, logr, ppc, red, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size >> logn, q, psi, mode)
+    if rc:
+        raise RuntimeError(f"emu_spectrum rc={rc}")
+    return out
 
 
 def transform(wb, logn, logr, ppc, red, x, q, root, mode, reduce_input=0):

@@ -109,6 +109,69 @@ template <class C, int NA, bool RED> struct Emu {
         }
     }
 
+    // transform-domain kernels (spectrum_forward_kernel / spectrum_inverse_kernel / polymul_spectrum_kernel)
+    void spectrum_forward(const W *in, W *out, size_t batch) {
+        tile.assign((size_t)C::PPC * C::N, 0);
+        x.assign((size_t)T * NA * C::R, 0);
+        const size_t ctas = (batch + C::PPC - 1) / C::PPC;
+        for (size_t cta = 0; cta < ctas; ++cta) {
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                row_load<C>(X(t)[0], in + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch);
+            }
+            forward_from<0>();
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                if (poly >= batch) continue;
+                for (int k = 0; k < C::R; ++k)
+                    out[poly * C::N + (k << C::LOGP) + (t & (C::P - 1))] = csub(shoup_mul(X(t)[0][k], (W)1, mod.one_p, mod.nq), mod.q);
+            }
+        }
+    }
+    void spectrum_inverse(const W *in, W *out, size_t batch, const Tw<W> *post) {
+        tile.assign((size_t)C::PPC * C::N, 0);
+        fa.assign((size_t)T * C::R, 0);
+        const size_t ctas = (batch + C::PPC - 1) / C::PPC;
+        for (size_t cta = 0; cta < ctas; ++cta) {
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                row_load<C>(F(t), in + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch);
+            }
+            dit_from<1, 0>(tb.inv);
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                row_store_scaled<C, 1>(F(t), out + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, post, Tw<W>{0, 0}, mod);
+            }
+        }
+    }
+    void polymul_spectrum(const W *a, const W *bspec, W *c, size_t batch, size_t b_stride) {
+        tile.assign((size_t)C::PPC * C::N, 0);
+        x.assign((size_t)T * NA * C::R, 0);
+        fa.assign((size_t)T * C::R, 0);
+        const size_t ctas = (batch + C::PPC - 1) / C::PPC;
+        for (size_t cta = 0; cta < ctas; ++cta) {
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                row_load<C>(X(t)[0], a + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch);
+            }
+            forward_from<0>();
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                const W *brow = bspec + (poly < batch ? poly * b_stride : 0);
+                for (int k = 0; k < C::R; ++k) {
+                    W u = X(t)[0][k];
+                    if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
+                    F(t)[k] = mont_mul(u, brow[(k << C::LOGP) + (t & (C::P - 1))], mod);
+                }
+            }
+            dit_from<2, 0>(tb.inv);
+            for (int t = 0; t < T; ++t) {
+                const size_t poly = cta * C::PPC + (t >> C::LOGP);
+                row_store_scaled<C, 1>(F(t), c + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, tb.post, Tw<W>{0, 0}, mod);
+            }
+        }
+    }
+
     // standalone transform kernel body (transform_kernel in kernels.cuh)
     void transform(const W *in, W *out, size_t batch, const TransformTables<W> &tt) {
         tile.assign((size_t)C::PPC * C::N, 0);
@@ -162,6 +225,37 @@ int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q,
     return 0;
 }
 
+// mode 0: spec = forward(a), out = inverse(spec); 1: out = polymul_spectrum(a, forward(b)), one spectrum per row;
+// 2: the same with the spectrum of b's row 0 shared by the batch; 3: out = forward(a) (the raw spectrum)
+template <class C, bool RED>
+int run_spectrum(const void *a, const void *b, void *out, size_t batch, uint64_t q, uint64_t psi, int mode) {
+    using W = typename C::W;
+    constexpr int BITS = WordTraits<W>::BITS;
+    if (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN)) return -2;
+    const uint64_t omega = host::mulmod(psi, psi, q), n_inv = host::modinv(C::N % q, q);
+    auto fwd = host::fwd_pyramid<W>(psi, C::N, q);
+    auto last = host::fwd_last_table<W>(fwd, C::LOGN, C::LOGR);
+    auto inv = host::dit_pyramid<W>(host::modinv(omega, q), C::N, q);
+    auto post_mont = host::scaled_powers<W>(host::modinv(psi, q), host::mulmod(n_inv, (uint64_t)((((host::u128)1) << BITS) % q), q), C::N, q);
+    auto post_plain = host::scaled_powers<W>(host::modinv(psi, q), n_inv, C::N, q);
+    Emu<C, 1, RED> e;
+    e.tb.fwd_pyr = fwd.data();
+    e.tb.fwd_last = last.data();
+    e.tb.post = post_mont.data();
+    e.tb.inv.pyr = inv.data();
+    for (int i = 0; i < MAX_R && i < C::N; ++i) { e.tb.fwd_head[i] = fwd[i]; e.tb.inv.head[i] = inv[i]; }
+    e.mod = host::make_mod<W>(q, C::LOGN);
+    std::vector<W> spec((size_t)batch * C::N);
+    if (mode == 0 || mode == 3) {
+        e.spectrum_forward((const W *)a, mode == 3 ? (W *)out : spec.data(), batch);
+        if (mode == 0) e.spectrum_inverse(spec.data(), (W *)out, batch, post_plain.data());
+    } else {
+        e.spectrum_forward((const W *)b, spec.data(), mode == 2 ? 1 : batch);
+        e.polymul_spectrum((const W *)a, spec.data(), (W *)out, batch, mode == 2 ? 0 : C::N);
+    }
+    return 0;
+}
+
 // mode 0: cg_ntt (root = omega); 1: cg_intt; 2: twisted forward; 3: twisted inverse
 template <class C, bool RED>
 int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t root, int mode, int reduce_input) {
@@ -195,7 +289,26 @@ int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t 
     if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && red == RED_)                    \
         return run_transform<Cfg<WT, LN, LR, PPC>, (RED_ != 0)>(in, out, batch, q, root, mode, reduce_input);
 
+#define SPEC_CASE(WB, WT, LN, LR, PPC, RED_)                                                           \
+    if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && red == RED_)                    \
+        return run_spectrum<Cfg<WT, LN, LR, PPC>, (RED_ != 0)>(a, b, out, batch, q, psi, mode);
+
 extern "C" {
+
+// the shapes of tiny-ntt_b200/csrc/spectrum.cu
+int emu_spectrum(int word_bytes, int logn, int logr, int ppc, int red, const void *a, const void *b, void *out, size_t batch,
+                 uint64_t q, uint64_t psi, int mode) {
+    SPEC_CASE(4, uint32_t, 8, 4, 16, 0)
+    SPEC_CASE(4, uint32_t, 10, 5, 8, 0)
+    SPEC_CASE(4, uint32_t, 12, 4, 1, 0)
+    SPEC_CASE(8, uint64_t, 8, 4, 16, 0)
+    SPEC_CASE(8, uint64_t, 8, 4, 16, 1)
+    SPEC_CASE(8, uint64_t, 10, 4, 4, 0)
+    SPEC_CASE(8, uint64_t, 10, 4, 4, 1)
+    SPEC_CASE(8, uint64_t, 12, 4, 1, 0)
+    SPEC_CASE(8, uint64_t, 12, 4, 1, 1)
+    return -1;
+}
 
 int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, const void *a, const void *b, void *c,
                 size_t batch, uint64_t q, uint64_t psi) {

@@ -118,8 +118,8 @@ def test_batch_size_dispatch_cluster_and_small_shapes(tag):
     npdt = np.uint32 if plan.word_bytes == 4 else np.uint64
     sdt = np.int32 if plan.word_bytes == 4 else np.int64
     rng = np.random.default_rng(11)
-    edges = sorted({1, 2, plan.cluster_batch_max, plan.cluster_batch_max + 1, max(plan.small_batch_max, 1),
-                    max(plan.small_batch_max, 1) + 1})
+    edges = sorted({1, 2, max(plan.cluster_batch_max, 1), plan.cluster_batch_max + 1, max(plan.small_batch_max, 1),
+                    plan.small_batch_max + 1, 150})
     for rows in edges:
         a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
         b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
@@ -137,3 +137,45 @@ def test_batch_size_dispatch_cluster_and_small_shapes(tag):
     tntt.lib().tntt_plan_info_get(plan._h, __import__("ctypes").byref(info))
     assert info.cluster_variant == -1 and info.small_variant == -1
     tntt.clear_plan_cache()
+
+
+@pytest.mark.parametrize("tag", ["dilithium", "n1024_24", "n4096_24", "n4096_60"])
+def test_transform_domain_api(tag):
+    # operands kept as spectra (tntt_spectrum_forward / _inverse / tntt_polymul_spectrum): every route to the
+    # product gives the oracle's bits
+    import tntt
+
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    plan = tntt.get_plan(n, q, psi, True)
+    assert plan.spectrum == 1
+    co = COracle()
+    npdt = np.uint32 if plan.word_bytes == 4 else np.uint64
+    sdt = np.int32 if plan.word_bytes == 4 else np.int64
+    rng = np.random.default_rng(5)
+    rows = 37
+    a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    a[1], b[1] = O.make_poly(tag, 1), O.make_poly(tag, 2)
+    dev = lambda v: torch.from_numpy(np.ascontiguousarray(v).astype(npdt).view(sdt)).cuda()      # noqa: E731
+    host = lambda t: t.cpu().numpy().view(npdt).astype(np.uint64)                                # noqa: E731
+    ta, tb = dev(a), dev(b)
+    want = co.nwc_poly_mult(a, b, psi, q, threads=8)
+    sa, sb = tntt.forward_spectrum(plan, ta), tntt.forward_spectrum(plan, tb)
+    assert host(sa).max() < q
+    assert sorted(host(sa)[1].tolist()) == sorted(host(tntt.forward(plan, ta[1:2], twist=True))[0].tolist())
+    assert (host(tntt.inverse_spectrum(plan, sa)) == a).all()                                     # round trip
+    assert (host(tntt.inverse_spectrum(plan, tntt.pointwise(plan, sa, sb))) == want).all()        # all in the transform domain
+    assert (host(tntt.polymul_spectrum(plan, ta, sb)) == want).all()                              # one operand cached
+    shared = co.nwc_poly_mult(a, np.broadcast_to(b[1], a.shape).copy(), psi, q, threads=8)
+    assert (host(tntt.polymul_spectrum(plan, ta, sb[1])) == shared).all()                         # one spectrum for the batch
+    assert (host(tntt.polymul_spectrum(plan, ta, sb[1:2])) == shared).all()
+    assert host(tntt.polymul_spectrum(plan, ta[:1], sb[:1])).tolist() == want[:1].tolist()        # batch of one
+    with pytest.raises(ValueError):
+        tntt.polymul_spectrum(plan, ta, sb[:2])
+    # plans without a fused size or without psi have no spectrum kernels: a loud error, no fallback
+    small = tntt.get_plan(64, 8380417, pow(1239911, 4, 8380417), True)
+    assert small.spectrum == 0
+    with pytest.raises(tntt.TnttError):
+        tntt.forward_spectrum(small, torch.zeros((1, 64), dtype=torch.int32, device="cuda"))

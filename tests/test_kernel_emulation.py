@@ -139,3 +139,30 @@ def test_host_number_theory_helpers():
     assert L.emu_lazy_full_ok(4, (1 << 30) - 35, 12) == 0
     assert L.emu_lazy_full_ok(8, 1152921504606830593, 12) == 0  # the 60-bit modulus needs the per-pass reduction
     assert L.emu_lazy_full_ok(8, (1 << 50) - 27, 12) == 1
+
+
+SPEC = [(4, 8, 4, 16, 0, "dilithium"), (4, 10, 5, 8, 0, "n1024_24"), (4, 12, 4, 1, 0, "n4096_24"),
+        (8, 8, 4, 16, 1, "dilithium"), (8, 10, 4, 4, 0, "n1024_24"), (8, 12, 4, 1, 0, "n4096_24"),
+        (8, 12, 4, 1, 1, "n4096_60")]
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,red,tag", SPEC)
+def test_emulated_transform_domain_kernels(wb, logn, logr, ppc, red, tag, co):
+    # spectrum_forward / spectrum_inverse / polymul_spectrum kernel bodies (csrc/kernels.cuh) replayed on the CPU
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    rng = np.random.default_rng(logn * 7 + wb)
+    batch = ppc + 2
+    a = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    a[1], b[1] = O.make_poly(tag, 1), O.make_poly(tag, 2)
+    assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 0).astype(np.uint64) == a).all()          # round trip
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 1).astype(np.uint64) == want).all()       # per-row spectra
+    shared = co.nwc_poly_mult(a, np.broadcast_to(b[0], a.shape).copy(), psi, q, threads=4)
+    assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 2).astype(np.uint64) == shared).all()     # one shared spectrum
+    spec = emu.spectrum(wb, logn, logr, ppc, red, a[:1], b[:1], q, psi, 3).astype(np.uint64)[0]
+    assert spec.max() < q                                                                                   # canonical
+    assert sorted(spec.tolist()) == sorted(O.forward_negacyclic([int(v) for v in a[0]], psi, q))            # a permutation of ntt(twist(a))
+    assert emu.lib().emu_range_violations() == 0

@@ -88,6 +88,7 @@ struct tntt_plan {
     Tw<uint32_t> head32[3][MAX_R] = {};   // [0] fwd_pyr, [1] inv_pyr, [2] cyc_fwd_pyr
     Tw<uint64_t> head64[3][MAX_R] = {};
     const TransformVariant *xform = nullptr;
+    const SpectrumVariant *spectrum = nullptr;
     // host pipeline
     std::mutex pipe_mu;
     static constexpr int kSlots = 3;
@@ -247,6 +248,19 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
                 break;
             }
     }
+    if (I.has_psi) {
+        int c = 0;
+        const SpectrumVariant *sv = spectrum_variants(&c);
+        for (int i = 0; i < c; ++i)
+            if (sv[i].word_bytes == I.word_bytes && sv[i].logn == (int)I.logn && sv[i].red == I.lazy_reduce && p->fwd_last[sv[i].logr]) {
+                if (sv[i].red && !host::lazy_pass_ok<uint64_t>(q, sv[i].logr)) continue;
+                cudaError_t e = sv[i].prepare();
+                if (e != cudaSuccess) { tntt_plan_destroy(p); return fail(TNTT_CUDA_ERROR, "prepare %s: %s", sv[i].name, cudaGetErrorString(e)); }
+                p->spectrum = &sv[i];
+                break;
+            }
+    }
+    I.spectrum = p->spectrum ? 1 : 0;
     const std::vector<PolymulVariant> &vs = all_variants();
     for (size_t i = 0; i < vs.size(); ++i)
         if (tntt_variant_matches(p, (int)i)) {
@@ -331,6 +345,39 @@ template <typename W> int launch_variant(const tntt_plan *p, const PolymulVarian
     else { memcpy(tb.fwd_head, p->head64[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head64[1], sizeof tb.inv.head); }
     CUDA_TRY(v.launch(a, b, c, batch, &tb, p->mod(), st));
     return TNTT_OK;
+}
+
+template <typename W> void fill_polymul_tables(const tntt_plan *p, int logr, PolymulTables<W> &tb) {
+    tb.fwd_pyr = (const Tw<W> *)p->fwd_pyr;
+    tb.fwd_last = (const Tw<W> *)p->fwd_last[logr];
+    tb.post = (const Tw<W> *)p->post_mont;
+    tb.inv.pyr = (const Tw<W> *)p->inv_pyr;
+    if constexpr (sizeof(W) == 4) { memcpy(tb.fwd_head, p->head32[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head32[1], sizeof tb.inv.head); }
+    else { memcpy(tb.fwd_head, p->head64[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head64[1], sizeof tb.inv.head); }
+}
+// op: 0 = forward, 1 = inverse, 2 = polymul with b in the transform domain
+template <typename W> int spectrum_op(const tntt_plan *p, int op, const void *a, const void *b, void *out, size_t batch,
+                                      size_t b_stride, cudaStream_t st) {
+    PolymulTables<W> tb;
+    fill_polymul_tables<W>(p, p->spectrum->logr, tb);
+    cudaError_t e = cudaSuccess;
+    if (op == 0) e = p->spectrum->forward(a, out, batch, &tb, p->mod(), st);
+    else if (op == 1) e = p->spectrum->inverse(a, out, batch, &tb, p->post_untwist, p->mod(), st);
+    else e = p->spectrum->polymul(a, b, out, batch, b_stride, &tb, p->mod(), st);
+    if (e != cudaSuccess) return fail(TNTT_CUDA_ERROR, "%s: %s", p->spectrum->name, cudaGetErrorString(e));
+    return TNTT_OK;
+}
+int spectrum_entry(const tntt_plan *p, int op, const void *a, const void *b, void *out, size_t batch, size_t b_rows, void *stream) {
+    int rc = check_io(p, a, op == 2 ? b : a, batch);
+    if (rc) return rc;
+    if (!p->spectrum) return fail(TNTT_UNSUPPORTED_N, "no transform-domain kernels for this plan (needs psi and a fused size: n in {256, 1024, 4096})");
+    if (batch == 0) return TNTT_OK;
+    if (!out || ((uintptr_t)out & 15)) return fail(TNTT_BAD_ARG, "output must be a 16-byte aligned device pointer");
+    if (op == 2 && b_rows != 1 && b_rows != batch) return fail(TNTT_BAD_ARG, "b_rows must be 1 (shared spectrum) or the batch size");
+    DeviceSetter ds(p->info.device);
+    const size_t b_stride = (op == 2 && b_rows == batch) ? p->info.n : 0;   // 0: every row reads the one shared spectrum
+    return p->info.word_bytes == 4 ? spectrum_op<uint32_t>(p, op, a, b, out, batch, b_stride, (cudaStream_t)stream)
+                                   : spectrum_op<uint64_t>(p, op, a, b, out, batch, b_stride, (cudaStream_t)stream);
 }
 
 int generic_polymul(const tntt_plan *p, const void *a, const void *b, void *c, size_t batch, cudaStream_t st) {
@@ -443,6 +490,17 @@ int tntt_pointwise(const tntt_plan *p, const void *a, const void *b, void *c, si
     DeviceSetter ds(p->info.device);
     CUDA_TRY(launch_pointwise(p->info.word_bytes, a, b, c, batch * p->info.n, p->mod(), (cudaStream_t)stream));
     return TNTT_OK;
+}
+
+int tntt_spectrum_forward(const tntt_plan *p, const void *in, void *out, size_t batch, void *stream) {
+    return spectrum_entry(p, 0, in, nullptr, out, batch, 0, stream);
+}
+int tntt_spectrum_inverse(const tntt_plan *p, const void *in, void *out, size_t batch, void *stream) {
+    return spectrum_entry(p, 1, in, nullptr, out, batch, 0, stream);
+}
+int tntt_polymul_spectrum(const tntt_plan *p, const void *a, const void *b_spectrum, void *c, size_t batch, size_t b_rows,
+                          void *stream) {
+    return spectrum_entry(p, 2, a, b_spectrum, c, batch, b_rows, stream);
 }
 
 int tntt_variant_count(void) { return (int)all_variants().size(); }

@@ -31,6 +31,19 @@ struct TransformVariant {
     cudaError_t (*prepare)();
 };
 
+// transform-domain kernels of one plan shape (spectrum.cu)
+struct SpectrumVariant {
+    const char *name;
+    int word_bytes, logn, logr, ppc, red;
+    cudaError_t (*forward)(const void *in, void *out, size_t batch, const void *tables, const void *mod, cudaStream_t st);
+    cudaError_t (*inverse)(const void *in, void *out, size_t batch, const void *tables, const void *post, const void *mod,
+                           cudaStream_t st);
+    cudaError_t (*polymul)(const void *a, const void *bspec, void *c, size_t batch, size_t b_stride, const void *tables,
+                           const void *mod, cudaStream_t st);
+    cudaError_t (*prepare)();
+};
+const SpectrumVariant *spectrum_variants(int *count);
+
 const PolymulVariant *polymul_variants_u32(int *count);
 const PolymulVariant *polymul_variants_u64(int *count);
 const PolymulVariant *polymul_variants_u64b(int *count);

@@ -605,6 +605,87 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Operands kept in the transform domain (one forward transform per operand, reused
+// across many products -- the RLWE use of the reference, reports/final-report.tex:571-610).
+//
+// A "spectrum" row is the negacyclic NTT of a polynomial in the order the fused kernel holds it in registers
+// between its last forward and first inverse pass, stored so that the access is the coalesced row pattern:
+// word k*P + t of the row = bit-reversed-order element t*R + k (R, P of the plan's spectrum shape).  It is
+// canonical ([0, q)), so tntt_pointwise applies to it directly (the product is order-agnostic).  Producing and
+// consuming spectra needs no bit reversal, no twist pass and no regrouping beyond the fused kernel's own:
+//   spectrum_forward_kernel  = the forward half of polymul_kernel          (ntt(twist(a)), cg_ntt.py:82-87)
+//   spectrum_inverse_kernel  = its inverse half                            (untwist(cg_intt(.)), cg_ntt.py:90-92)
+//   polymul_spectrum_kernel  = polymul_kernel with b's transform replaced by a load (b may be one shared row)
+// ---------------------------------------------------------------------------------------------
+template <class C, bool RED, int MINB>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
+                        const __grid_constant__ PolymulTables<typename C::W> tb,
+                        const __grid_constant__ Mod<typename C::W> mod) {
+    using W = typename C::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tile = reinterpret_cast<W *>(smem_raw);
+    const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
+    const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
+    const bool active = poly < batch;
+    const size_t off = active ? poly * C::N : 0;
+    W x[1][C::R];
+    row_load<C>(x[0], in + off, tid, active);
+    forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) {
+        const W v = csub(shoup_mul(x[0][k], (W)1, mod.one_p, mod.nq), mod.q);   // any word -> [0, q)
+        if (active) st_stream(out + off + (k << C::LOGP) + tid, v);
+    }
+}
+
+template <class C, bool RED, int MINB>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
+                        const __grid_constant__ DitTables<typename C::W> inv, const Tw<typename C::W> *__restrict__ post,
+                        const __grid_constant__ Mod<typename C::W> mod) {
+    using W = typename C::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tile = reinterpret_cast<W *>(smem_raw);
+    const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
+    const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
+    const bool active = poly < batch;
+    const size_t off = active ? poly * C::N : 0;
+    W x[C::R];
+    row_load<C>(x, in + off, tid, active);                      // spectrum order == the coalesced row pattern
+    dit_all<C, RED, 1, false, C::PREFETCH>(x, tile, pl, tid, inv, post, mod);   // canonical input: below one unit
+    row_store_scaled<C, 1>(x, out + off, tid, active, post, Tw<W>{0, 0}, mod);
+}
+
+// b_stride = N: one spectrum per row; b_stride = 0: one spectrum shared by the whole batch
+template <class C, bool RED, int MINB>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+polymul_spectrum_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ bspec,
+                        typename C::W *__restrict__ c, size_t batch, size_t b_stride,
+                        const __grid_constant__ PolymulTables<typename C::W> tb,
+                        const __grid_constant__ Mod<typename C::W> mod) {
+    using W = typename C::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tile = reinterpret_cast<W *>(smem_raw);
+    const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
+    const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
+    const bool active = poly < batch;
+    const size_t off = active ? poly * C::N : 0;
+    const W *brow = bspec + (active ? poly * b_stride : 0);
+    W x[1][C::R], fa[C::R];
+    row_load<C>(x[0], a + off, tid, active);
+    forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+    for (int k = 0; k < C::R; ++k) {
+        W u = x[0][k];
+        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
+        fa[k] = mont_mul(u, __ldg(brow + (k << C::LOGP) + tid), mod);     // < u*q/2^BITS + q: below two units
+    }
+    dit_all<C, RED, 2, false, C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod);
+    row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small batches: ONE polynomial pair per thread-block CLUSTER (N = 4096)
 //
 // With fewer rows than SMs the one-CTA-per-row kernel leaves most of the chip idle and a row's latency is

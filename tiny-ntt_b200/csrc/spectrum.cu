@@ -1,0 +1,64 @@
+// Transform-domain entry points: instantiations of spectrum_forward_kernel / spectrum_inverse_kernel /
+// polymul_spectrum_kernel (kernels.cuh) for the plan shapes that have a fused polymul.
+#include "common.h"
+
+namespace tntt {
+
+template <class C, bool RED, int MINB> struct SpectrumInst {
+    using W = typename C::W;
+    static constexpr size_t SMEM = (size_t)C::PPC * C::N * sizeof(W);
+    static unsigned ctas(size_t batch) { return (unsigned)((batch + C::PPC - 1) / C::PPC); }
+    static cudaError_t forward(const void *in, void *out, size_t batch, const void *tables, const void *mod, cudaStream_t st) {
+        spectrum_forward_kernel<C, RED, MINB><<<ctas(batch), C::THREADS, SMEM, st>>>(
+            static_cast<const W *>(in), static_cast<W *>(out), batch, *static_cast<const PolymulTables<W> *>(tables),
+            *static_cast<const Mod<W> *>(mod));
+        return cudaGetLastError();
+    }
+    static cudaError_t inverse(const void *in, void *out, size_t batch, const void *tables, const void *post, const void *mod,
+                               cudaStream_t st) {
+        spectrum_inverse_kernel<C, RED, MINB><<<ctas(batch), C::THREADS, SMEM, st>>>(
+            static_cast<const W *>(in), static_cast<W *>(out), batch, static_cast<const PolymulTables<W> *>(tables)->inv,
+            static_cast<const Tw<W> *>(post), *static_cast<const Mod<W> *>(mod));
+        return cudaGetLastError();
+    }
+    static cudaError_t polymul(const void *a, const void *bspec, void *c, size_t batch, size_t b_stride, const void *tables,
+                               const void *mod, cudaStream_t st) {
+        polymul_spectrum_kernel<C, RED, MINB><<<ctas(batch), C::THREADS, SMEM, st>>>(
+            static_cast<const W *>(a), static_cast<const W *>(bspec), static_cast<W *>(c), batch, b_stride,
+            *static_cast<const PolymulTables<W> *>(tables), *static_cast<const Mod<W> *>(mod));
+        return cudaGetLastError();
+    }
+    static cudaError_t prepare() {
+        cudaError_t e = cudaFuncSetAttribute(spectrum_forward_kernel<C, RED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_inverse_kernel<C, RED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(polymul_spectrum_kernel<C, RED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        return e;
+    }
+};
+
+#define TNTT_SPECTRUM_VARIANT(WT, WB, LN, LR, PPC, RED, MINB)                                                \
+    SpectrumVariant {                                                                                        \
+        "sp_u" #WB "_n" #LN "_r" #LR "_p" #PPC "_red" #RED, WB / 8, LN, LR, PPC, RED,                          \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::forward,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::inverse,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::polymul,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::prepare                                    \
+    }
+
+// one shape per (word, N, reduction mode): the spectrum order is part of the plan, not of a kernel variant
+static const SpectrumVariant kVariants[] = {
+    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 8, 4, 16, 0, 4),
+    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 10, 5, 8, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 12, 4, 1, 0, 4),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 8, 4, 16, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 8, 4, 16, 1, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 10, 4, 4, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 10, 4, 4, 1, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 12, 4, 1, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 12, 4, 1, 1, 3),
+};
+const SpectrumVariant *spectrum_variants(int *count) {
+    *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+    return kVariants;
+}
+}  // namespace tntt

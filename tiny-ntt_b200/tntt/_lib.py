@@ -20,6 +20,7 @@ SYMBOLS = (
     "tntt_cg_stage", "tntt_bit_reverse", "tntt_scale", "tntt_reduce", "tntt_butterfly_batch", "tntt_variant_count",
     "tntt_variant_describe", "tntt_variant_matches", "tntt_polymul_variant", "tntt_plan_set_default_variant",
     "tntt_microbench", "tntt_last_error", "tntt_version",
+    "tntt_spectrum_forward", "tntt_spectrum_inverse", "tntt_polymul_spectrum",
 )
 
 
@@ -30,7 +31,7 @@ class PlanInfo(C.Structure):
         ("barrett_k", C.c_int), ("barrett_mu", C.c_uint64), ("has_psi", C.c_int), ("omega_is_primitive", C.c_int),
         ("fused", C.c_int), ("lazy_reduce", C.c_int), ("default_variant", C.c_int), ("device", C.c_int),
         ("cluster_variant", C.c_int), ("cluster_batch_max", C.c_int), ("small_variant", C.c_int),
-        ("small_batch_max", C.c_int),
+        ("small_batch_max", C.c_int), ("spectrum", C.c_int),
     ]
 
 
@@ -65,6 +66,9 @@ def lib() -> C.CDLL:
     L.tntt_pointwise.argtypes = [vp, vp, vp, vp, sz, vp]
     L.tntt_polymul.argtypes = [vp, vp, vp, vp, sz, vp]
     L.tntt_polymul_host.argtypes = [vp, vp, vp, vp, sz]
+    L.tntt_spectrum_forward.argtypes = [vp, vp, vp, sz, vp]
+    L.tntt_spectrum_inverse.argtypes = [vp, vp, vp, sz, vp]
+    L.tntt_polymul_spectrum.argtypes = [vp, vp, vp, vp, sz, sz, vp]
     L.tntt_cg_stage.argtypes = [vp, vp, vp, sz, i, i, vp]
     L.tntt_bit_reverse.argtypes = [vp, vp, vp, sz, vp]
     L.tntt_scale.argtypes = [vp, vp, vp, sz, u64, vp]

@@ -105,6 +105,37 @@ def polymul(plan: Plan, a, b, out=None, variant: Optional[int] = None):
     return o
 
 
+def forward_spectrum(plan: Plan, x, out=None):
+    """Coefficients -> spectrum: ntt(twist(x)) of every row, canonical, in the plan's (opaque) spectrum order.
+    Keep operands in this form when they take part in many products (tntt_spectrum_forward)."""
+    t = _prep(plan, x, "x")
+    o = _out_like(t, out)
+    check(lib().tntt_spectrum_forward(plan._h, t.data_ptr(), o.data_ptr(), _rows(t), _stream(plan)))
+    return o
+
+
+def inverse_spectrum(plan: Plan, x, out=None):
+    """Spectrum -> coefficients: untwist(cg_intt(.)) of every row (tntt_spectrum_inverse)."""
+    t = _prep(plan, x, "x")
+    o = _out_like(t, out)
+    check(lib().tntt_spectrum_inverse(plan._h, t.data_ptr(), o.data_ptr(), _rows(t), _stream(plan)))
+    return o
+
+
+def polymul_spectrum(plan: Plan, a, b_spectrum, out=None):
+    """Negacyclic product a * b with b already in the transform domain (forward_spectrum).  ``b_spectrum`` has
+    either a's shape or a single row [n] / [1, n] shared by every row of a.  Bit-identical to polymul(a, b)."""
+    ta, tb = _prep(plan, a, "a"), _prep(plan, b_spectrum, "b_spectrum")
+    if ta.dtype != tb.dtype:
+        raise ValueError("a and b_spectrum must have the same dtype")
+    rows, brows = _rows(ta), _rows(tb)
+    if brows != rows and brows != 1:
+        raise ValueError("b_spectrum must have one row or as many rows as a")
+    o = _out_like(ta, out)
+    check(lib().tntt_polymul_spectrum(plan._h, ta.data_ptr(), tb.data_ptr(), o.data_ptr(), rows, brows, _stream(plan)))
+    return o
+
+
 def polymul_host(plan: Plan, a, b, out=None):
     """Host tensors in, host tensor out (pin them for full copy/compute overlap).  Blocking."""
     import torch

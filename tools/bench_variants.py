@@ -48,7 +48,12 @@ def main():
                               "polymul_per_s": rows / (ms * 1e-3), "GBps": bytes_ / (ms * 1e-3) / 1e9,
                               "agrees_with_first_variant": same}), flush=True)
         # standalone transforms
-        for name, fn in (("forward", lambda: tntt.forward(plan, a, out=c)),
+        spec = tntt.forward_spectrum(plan, b)
+        for name, fn in (("forward_spectrum", lambda: tntt.forward_spectrum(plan, a, out=c)),
+                         ("inverse_spectrum", lambda: tntt.inverse_spectrum(plan, spec, out=c)),
+                         ("polymul_spectrum", lambda: tntt.polymul_spectrum(plan, a, spec, out=c)),
+                         ("polymul_spectrum_shared", lambda: tntt.polymul_spectrum(plan, a, spec[0], out=c)),
+                         ("forward", lambda: tntt.forward(plan, a, out=c)),
                          ("forward_twist", lambda: tntt.forward(plan, a, twist=True, out=c)),
                          ("inverse_twist", lambda: tntt.inverse(plan, a, twist=True, out=c)),
                          ("pointwise", lambda: tntt.pointwise(plan, a, b, out=c))):
@@ -62,7 +67,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
-            nb = (3 if name == "pointwise" else 2) * p["n"] * plan.word_bytes * rows
+            nb = (3 if name in ("pointwise", "polymul_spectrum") else 2) * p["n"] * plan.word_bytes * rows
             print(json.dumps({"config": tag, "op": name, "rows": rows, "ms": ms, "rows_per_s": rows / (ms * 1e-3),
                               "GBps": nb / (ms * 1e-3) / 1e9}), flush=True)
         del a, b, c, ref
