@@ -200,6 +200,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    from tntt.shard import bind_host_thread_to_gpu
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_host_thread_to_gpu(local)   # staging buffers of the e2e leg stay next to this rank's GPU
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator is created; rank 0 must print
         # exactly one JSON line, so stdout is parked on /dev/null while the communicator comes up.
@@ -268,6 +271,33 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     total_rows = rows * world
     value = total_rows * args.steps / (ms * 1e-3)
+
+    # ---- the same work with operands kept in the transform domain (reported next to the headline)
+    extras = None
+    if plan.spectrum:
+        def timed(fn, reps=max(3, min(args.steps, 10))):
+            for _ in range(2):
+                fn()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(reps):
+                fn()
+            s1.record()
+            torch.cuda.synchronize()
+            return total_rows * reps / (max_over_ranks(s0.elapsed_time(s1)) * 1e-3)
+
+        spec = tntt.forward_spectrum(plan, b)
+        extras = {
+            "forward_spectrum_rows_per_s": timed(lambda: tntt.forward_spectrum(plan, a, out=c)),
+            "inverse_spectrum_rows_per_s": timed(lambda: tntt.inverse_spectrum(plan, spec, out=c)),
+            "polymul_spectrum_per_s": timed(lambda: tntt.polymul_spectrum(plan, a, spec, out=c)),
+            "pointwise_rows_per_s": timed(lambda: tntt.pointwise(plan, a, spec, out=c)),
+            "note": "one operand (or both) kept as a spectrum: tntt_spectrum_forward / tntt_polymul_spectrum / "
+                    "tntt_pointwise + tntt_spectrum_inverse; device-resident, whole job over all GPUs",
+        }
+        tntt.polymul(plan, a, b, out=c)      # restore c for the e2e parity check below
+        del spec
 
     # ---- end to end through the host-buffer entry point (pinned memory, H2D + kernel + D2H per step)
     e2e = None
@@ -339,6 +369,7 @@ def run_ours(args):
         int_roofline = {"error": str(exc)}
 
     cpu = None
+    os.sched_setaffinity(0, all_cpus)       # the CPU baseline gets every host core again
     if world == 1 and not args.no_cpu_baseline:
         ctx = cpu_reference_throughput(tag, seconds=10.0)
         t = time.perf_counter()
@@ -365,8 +396,9 @@ def run_ours(args):
         "dtype": "u64" if wb == 8 else "u32", "data": "synthetic",
         "config": {"workload": workload_name(tag), "rows_per_gpu": rows, "rows_total": total_rows,
                    "parallelism": f"batch-sharded x{world}, no collective", "kernel_variant": variant_desc,
+                   "host_affinity": numa,
                    "l2": "inputs exceed L2 (%.2f GB read per launch vs 126 MB)" % (2 * n * wb * rows / 1e9)},
-        "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu, "e2e": e2e, "transform_domain": extras,
         "gpu_launches": args.steps, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -50,3 +50,49 @@ def sum_over_ranks(value: float) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_thread_to_gpu(device: int) -> dict:
+    """Pin the calling process to the CPUs that sit next to GPU `device` (its PCIe root / NUMA node).
+
+    The host pipeline (tntt_polymul_host) streams 96 KB per polynomial over PCIe; when the feeding process
+    runs on the other socket, every pinned page is first-touched remotely and the copies cross the inter-socket
+    link.  One process per GPU, each bound to its GPU's `local_cpulist`, keeps the staging buffers local.
+    Returns what was done (for the benchmark's log); never raises -- an unknown topology just leaves the
+    affinity alone."""
+    import os
+
+    info = {"device": device, "bound": False}
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(os.path.join(base, "local_cpulist")) as fh:
+            local = _parse_cpulist(fh.read())
+        try:
+            with open(os.path.join(base, "numa_node")) as fh:
+                info["numa_node"] = int(fh.read().strip())
+        except (OSError, ValueError):
+            pass
+        allowed = os.sched_getaffinity(0)
+        target = (local & allowed) or set()
+        info["pci"] = bdf
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info["bound"] = True
+        info["cpus"] = len(target or allowed)
+    except Exception as exc:  # topology not visible (container without /sys, no such attribute, ...)
+        info["error"] = type(exc).__name__
+    return info
