@@ -566,7 +566,9 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     W fa[C::R];
     if constexpr (NA == 1) {
         W x[1][C::R];
-        W *stash = tile + C::PPC * C::N + threadIdx.x;
+        // STASH = 1: second shared tile; STASH = 2: the output row itself (global memory, stays in L2), which
+        // leaves the CTA with one tile of shared memory and the SM with a larger L1 for the twiddle tables
+        W *stash = (STASH == 2) ? (c + off + threadIdx.x) : (tile + C::PPC * C::N + threadIdx.x);
 #if defined(TNTT_X_PREFETCH_B)
         // b's row is needed one forward transform from now: pull it into L2 (one 128-byte line per thread)
         if (threadIdx.x * 16 < C::N) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + off + threadIdx.x * 16));

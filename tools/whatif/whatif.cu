@@ -87,7 +87,7 @@ int main(int argc, char **argv) {
     };
 #else
     auto kern = polymul_kernel<C, W_NA, true, W_MINB, W_STASH, W_TMA>;
-    const size_t smem = (size_t)(W_NA + W_STASH) * C::N * sizeof(W) + (W_TMA ? kTwBufBytes + 16 : 0);
+    const size_t smem = (size_t)(W_NA + (W_STASH == 1 ? 1 : 0)) * C::N * sizeof(W) + (W_TMA ? kTwBufBytes + 16 : 0);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kern));
     int bps = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, C::THREADS, smem));
