@@ -66,16 +66,44 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region.
 
+    NVML is queried in-process from a thread (one light call per quantity every 20 ms).  Spawning `nvidia-smi -lms`
+    for this stalls the GPU for a few milliseconds per query, which is visible in a 50 ms timed region; it is
+    only the fallback when the NVML binding is missing."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.thread = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            if os.environ.get("TNTT_BENCH_SAMPLER") == "smi":
+                raise RuntimeError("nvidia-smi sampler forced")
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -85,17 +113,42 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                try:
+                    watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    watts = float("nan")
+                self.rows.append((time.time(), sm, watts, mask))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0: float, t1: float):
+        names = [r[0] for r in self.REASONS]
+        if self.nvml:
+            time.sleep(0.03)
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            rows = [r for r in self.rows if t0 - 0.02 <= r[0] <= t1 + 0.03] or self.rows
+            sm = sorted(r[1] for r in rows)
+            power = [r[2] for r in rows if r[2] == r[2]]
+            reasons = sorted({name for r in rows for name, bit in self.REASONS if r[3] & bit})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                    "samples": len(sm), "power_w_max": max(power) if power else None, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons, power = [], None, set(), []
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
         for line in rows:
             f = [x.strip() for x in line.split(",")]
@@ -112,7 +165,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+                "samples": len(sm), "power_w_max": max(power) if power else None, "source": "nvidia-smi"}
 
 
 def cpu_reference_throughput(tag: str, seconds: float = 10.0):

@@ -91,7 +91,7 @@ struct tntt_plan {
     const SpectrumVariant *spectrum = nullptr;
     // host pipeline
     std::mutex pipe_mu;
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 4;
     cudaStream_t pipe_stream[kSlots] = {};
     void *pipe_buf[kSlots][3] = {};
     size_t pipe_rows = 0;
@@ -567,34 +567,57 @@ int tntt_polymul_host(tntt_plan *p, const void *a, const void *b, void *c, size_
     DeviceSetter ds(p->info.device);
     std::lock_guard<std::mutex> lock(p->pipe_mu);
     const size_t row_bytes = (size_t)p->info.n * p->info.word_bytes;
-    // chunk: 32 MiB per operand by default (measured best on PCIe gen5; TNTT_HOST_CHUNK_MB overrides)
-    size_t chunk_mb = 32;
+    // Chunks ramp up from 1/16 of the full chunk, stay at the full chunk, and ramp down again: the first kernel
+    // starts after a short copy and the last kernel + copy-back is short, so that a blocking call is PCIe-bound
+    // for all but ~0.2 ms (a fixed chunk size pays one whole chunk of H2D before, and one of D2H after, the
+    // overlapped part).  Full chunk: 64 MiB per operand, measured best on PCIe gen5 (TNTT_HOST_CHUNK_MB overrides).
+    size_t chunk_mb = 64;
     if (const char *env = getenv("TNTT_HOST_CHUNK_MB")) { const long v = atol(env); if (v >= 1 && v <= 1024) chunk_mb = (size_t)v; }
-    size_t rows = (chunk_mb << 20) / row_bytes;
-    if (rows < 1) rows = 1;
-    if (rows > batch) rows = batch;
-    if (p->pipe_rows != rows) {
+    size_t full = (chunk_mb << 20) / row_bytes;
+    if (full < 1) full = 1;
+    if (full > batch) full = batch;
+    if (p->pipe_rows < full) {
         for (int s = 0; s < tntt_plan::kSlots; ++s) {
             if (!p->pipe_stream[s]) CUDA_TRY(cudaStreamCreateWithFlags(&p->pipe_stream[s], cudaStreamNonBlocking));
             for (int k = 0; k < 3; ++k) {
                 if (p->pipe_buf[s][k]) CUDA_TRY(cudaFree(p->pipe_buf[s][k]));
                 p->pipe_buf[s][k] = nullptr;
-                CUDA_TRY(cudaMalloc(&p->pipe_buf[s][k], rows * row_bytes));
+                CUDA_TRY(cudaMalloc(&p->pipe_buf[s][k], full * row_bytes));
             }
         }
-        p->pipe_rows = rows;
+        p->pipe_rows = full;
+    }
+    std::vector<size_t> head, tail;
+    {
+        const size_t first = full / 16 > 0 ? full / 16 : 1;
+        size_t h = first, t = first, rem = batch;
+        while (rem) {
+            size_t n = h < rem ? h : rem;
+            head.push_back(n);
+            rem -= n;
+            h = 2 * h < full ? 2 * h : full;
+            if (rem && t < full) {
+                n = t < rem ? t : rem;
+                tail.push_back(n);
+                rem -= n;
+                t = 2 * t < full ? 2 * t : full;
+            }
+        }
+        head.insert(head.end(), tail.rbegin(), tail.rend());
     }
     const char *pa = (const char *)a, *pb = (const char *)b;
     char *pc = (char *)c;
     int slot = 0;
-    for (size_t r0 = 0; r0 < batch; r0 += rows, slot = (slot + 1) % tntt_plan::kSlots) {
-        const size_t nr = batch - r0 < rows ? batch - r0 : rows;
+    size_t r0 = 0;
+    for (const size_t nr : head) {
         cudaStream_t st = p->pipe_stream[slot];
         CUDA_TRY(cudaMemcpyAsync(p->pipe_buf[slot][0], pa + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(p->pipe_buf[slot][1], pb + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st));
         int rc = tntt_polymul(p, p->pipe_buf[slot][0], p->pipe_buf[slot][1], p->pipe_buf[slot][2], nr, st);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(pc + r0 * row_bytes, p->pipe_buf[slot][2], nr * row_bytes, cudaMemcpyDeviceToHost, st));
+        r0 += nr;
+        slot = (slot + 1) % tntt_plan::kSlots;
     }
     for (int s = 0; s < tntt_plan::kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(p->pipe_stream[s]));
     return TNTT_OK;

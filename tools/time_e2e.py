@@ -11,7 +11,7 @@ rows = 8192
 a = torch.randint(0, p["q"], (rows, p["n"]), dtype=torch.int64).pin_memory()
 b = torch.randint(0, p["q"], (rows, p["n"]), dtype=torch.int64).pin_memory()
 c = torch.empty_like(a).pin_memory()
-for mb in (8, 16, 32, 64, 128, 256):
+for mb in (2, 4, 8, 16, 32, 64, 128):
     os.environ["TNTT_HOST_CHUNK_MB"] = str(mb)
     tntt.polymul_host(plan, a, b, out=c)
     t = time.perf_counter()
