@@ -373,7 +373,7 @@ def run_ours(args):
         e2e = {"value": e_rows * world * e_steps / (e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": 2 * e_rows * bytes_row, "d2h_bytes_per_step": e_rows * bytes_row,
                "rows_per_step_per_gpu": e_rows, "steps": e_steps, "ms_per_step": e_ms / e_steps,
-               "api": "tntt_polymul_host (pinned host buffers, 3-stream chunked H2D/kernel/D2H)"}
+               "api": "tntt_polymul_host (pinned host buffers; H2D / kernel / D2H pipelined over 4 streams, ramped chunks)"}
 
     if rank != 0:
         if world > 1:

@@ -54,6 +54,12 @@ def test_rns_product_matches_bigint_schoolbook():
         assert got[r] == O.schoolbook_negacyclic(big_a[r], big_b[r], ctx.Q)
     # transform-domain round trip per limb
     assert torch.equal(ctx.inverse(ctx.forward(a)), a)
+    # operands kept as spectra: same products
+    sb = ctx.forward_spectrum(b)
+    assert torch.equal(ctx.polymul_spectrum(a, sb), c)
+    assert torch.equal(ctx.inverse_spectrum(ctx.pointwise(ctx.forward_spectrum(a), sb)), c)
+    shared = ctx.polymul_spectrum(a, sb[:, :1])
+    assert torch.equal(shared, ctx.polymul(a, b[:, :1].expand_as(b).contiguous()))
 
 
 def test_tma_variant_agrees_and_is_listed():

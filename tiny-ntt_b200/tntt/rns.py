@@ -85,6 +85,35 @@ class RnsContext:
             ops.inverse(plan, ta[l], twist=twist, out=o[l])
         return o
 
+    # ---- operands kept in the transform domain (one spectrum per limb; see ops.forward_spectrum) ----
+    def _per_limb(self, fn, a, out, *rest):
+        import torch
+
+        ta = ops.as_tensor(a)
+        self._check(ta, "a")
+        o = torch.empty_like(ta) if out is None else out
+        for l, plan in enumerate(self.plans):
+            fn(plan, ta[l], *[r[l] for r in rest], out=o[l])
+        return o
+
+    def forward_spectrum(self, a, out=None):
+        return self._per_limb(ops.forward_spectrum, a, out)
+
+    def inverse_spectrum(self, a, out=None):
+        return self._per_limb(ops.inverse_spectrum, a, out)
+
+    def pointwise(self, a, b, out=None):
+        tb = ops.as_tensor(b)
+        self._check(tb, "b")
+        return self._per_limb(ops.pointwise, a, out, tb)
+
+    def polymul_spectrum(self, a, b_spectrum, out=None):
+        """out[l] = a[l] * b[l] with b given as per-limb spectra, shape [L, B, N] or [L, 1, N] (shared by the batch)."""
+        tb = ops.as_tensor(b_spectrum)
+        if tb.dim() != 3 or tb.shape[0] != len(self.plans) or tb.shape[-1] != self.n:
+            raise ValueError(f"b_spectrum must have shape [L={len(self.plans)}, B or 1, N={self.n}]")
+        return self._per_limb(ops.polymul_spectrum, a, out, tb)
+
     # ---- host-side helpers (tests, small data) ------------------------------------------------
     def decompose(self, coeffs: Sequence[Sequence[int]]):
         """[B][N] big integers -> [L, B, N] residues (numpy, word dtype)."""
