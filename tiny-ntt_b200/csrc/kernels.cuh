@@ -418,14 +418,21 @@ constexpr int kTwBufBytes = 65536;   // shared twiddle buffer of the TMA variant
 // ---------------------------------------------------------------------------------------------
 // regroup registers through the shared tile: layout LO_FROM -> LO_TO
 // ---------------------------------------------------------------------------------------------
+// A polynomial's region of the tile is touched only by the P threads that own the polynomial.  When those sit
+// inside one warp (N = 1024 with 32 coefficients per thread, N = 256), a warp barrier orders the exchange and
+// the other warps of the CTA are not held up.
+template <class C> __device__ __forceinline__ void tile_sync() {
+    if constexpr (C::P <= 32) __syncwarp();
+    else __syncthreads();
+}
 template <class C, int LO_FROM, int LO_TO>
 __device__ __forceinline__ void exchange(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid) {
 #if defined(TNTT_X_NO_EXCHANGE)
     return;   // what-if only: wrong results
 #endif
-    __syncthreads();  // everybody is done reading the tile's previous contents
+    tile_sync<C>();  // everybody is done reading the tile's previous contents
     tile_write<C, LO_FROM>(x, tile, pl, tid);
-    __syncthreads();
+    tile_sync<C>();
     tile_read<C, LO_TO>(x, tile, pl, tid);
 }
 
@@ -507,14 +514,15 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
 #else
         if constexpr (PASS > 0) {
 #endif
-            __syncthreads();  // everybody is done reading the tile (and, for PASS 1, the forward twiddle buffer)
+            if constexpr (TMA) __syncthreads();  // everybody is done reading the tile and, for PASS 1, the forward twiddle buffer
+            else tile_sync<C>();
             if constexpr (TMA && PASS == 1) {
                 constexpr int first = 1 << C::inv_blo(C::NPASS - 1);
                 if (threadIdx.x == 0)
                     tma->issue(dt.pyr + first, (unsigned)((C::N - first) * sizeof(Tw<typename C::W>)));
             }
             tile_write<C, C::inv_lo(PASS - 1)>(x, tile, pl, tid);
-            __syncthreads();
+            tile_sync<C>();
             tile_read<C, C::inv_lo(PASS)>(x, tile, pl, tid);
         }
         if constexpr (PASS + 2 == C::NPASS && PF && !TMA) prefetch_dit_last<C>(tid, dt.pyr);
@@ -824,7 +832,7 @@ transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict
         else if (tb.reduce_input) x[k] = shoup_mul(x[k], (W)1, mod.one_p, mod.nq);
         tile[C::spos(pl * C::N + bitrev_n(e, C::LOGN))] = x[k];
     }
-    __syncthreads();
+    tile_sync<C>();
     tile_read<C, 0>(x, tile, pl, tid);
     dit_all<C, RED, 2, false, true>(x, tile, pl, tid, tb.dit, tb.post, mod);   // short kernel: latency-bound without it (measured 2x)
     row_store_scaled<C>(x, out + off, tid, active, tb.post, tb.post_uniform, mod);
