@@ -110,7 +110,7 @@ template <class C, int NA, bool RED> struct Emu {
     }
 
     // transform-domain kernels (spectrum_forward_kernel / spectrum_inverse_kernel / polymul_spectrum_kernel)
-    void spectrum_forward(const W *in, W *out, size_t batch) {
+    void spectrum_forward(const W *in, W *out, size_t batch, bool natural = false) {
         tile.assign((size_t)C::PPC * C::N, 0);
         x.assign((size_t)T * NA * C::R, 0);
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
@@ -123,24 +123,31 @@ template <class C, int NA, bool RED> struct Emu {
             for (int t = 0; t < T; ++t) {
                 const size_t poly = cta * C::PPC + (t >> C::LOGP);
                 if (poly >= batch) continue;
-                for (int k = 0; k < C::R; ++k)
-                    out[poly * C::N + (k << C::LOGP) + (t & (C::P - 1))] = csub(shoup_mul(X(t)[0][k], (W)1, mod.one_p, mod.nq), mod.q);
+                for (int k = 0; k < C::R; ++k) {
+                    const int tid = t & (C::P - 1);
+                    const size_t idx = natural ? (size_t)((cbitrev(k, C::LOGR) << C::LOGP) | bitrev_n(tid, C::LOGP)) : (size_t)((k << C::LOGP) + tid);
+                    out[poly * C::N + idx] = csub(shoup_mul(X(t)[0][k], (W)1, mod.one_p, mod.nq), mod.q);
+                }
             }
         }
     }
-    void spectrum_inverse(const W *in, W *out, size_t batch, const Tw<W> *post) {
+    void spectrum_inverse(const W *in, W *out, size_t batch, const Tw<W> *post, bool natural = false, Tw<W> uniform = Tw<W>{0, 0}) {
         tile.assign((size_t)C::PPC * C::N, 0);
         fa.assign((size_t)T * C::R, 0);
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
         for (size_t cta = 0; cta < ctas; ++cta) {
             for (int t = 0; t < T; ++t) {
                 const size_t poly = cta * C::PPC + (t >> C::LOGP);
-                row_load<C>(F(t), in + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch);
+                if (!natural) row_load<C>(F(t), in + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch);
+                else
+                    for (int k = 0; k < C::R; ++k)
+                        F(t)[k] = poly < batch ? in[poly * C::N + ((cbitrev(k, C::LOGR) << C::LOGP) | bitrev_n(t & (C::P - 1), C::LOGP))] : (W)0;
             }
             dit_from<1, 0>(tb.inv);
             for (int t = 0; t < T; ++t) {
                 const size_t poly = cta * C::PPC + (t >> C::LOGP);
-                row_store_scaled<C, 1>(F(t), out + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, post, Tw<W>{0, 0}, mod);
+                if (post) row_store_scaled<C, 1>(F(t), out + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, post, Tw<W>{0, 0}, mod);
+                else row_store_scaled<C, 0>(F(t), out + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, nullptr, uniform, mod);
             }
         }
     }
@@ -246,6 +253,18 @@ int run_spectrum(const void *a, const void *b, void *out, size_t batch, uint64_t
     for (int i = 0; i < MAX_R && i < C::N; ++i) { e.tb.fwd_head[i] = fwd[i]; e.tb.inv.head[i] = inv[i]; }
     e.mod = host::make_mod<W>(q, C::LOGN);
     std::vector<W> spec((size_t)batch * C::N);
+    if (mode >= 4) {   // natural-order transforms: 4 = ntt(twist(a)), 5 = cg_ntt(a), 6 = twisted inverse, 7 = cg_intt
+        auto cyc = host::fwd_pyramid_cyclic<W>(omega, C::N, q);
+        auto cyc_last = host::fwd_last_table<W>(cyc, C::LOGN, C::LOGR);
+        if (mode == 5) {
+            e.tb.fwd_pyr = cyc.data();
+            e.tb.fwd_last = cyc_last.data();
+            for (int i = 0; i < MAX_R && i < C::N; ++i) e.tb.fwd_head[i] = cyc[i];
+        }
+        if (mode <= 5) e.spectrum_forward((const W *)a, (W *)out, batch, true);
+        else e.spectrum_inverse((const W *)a, (W *)out, batch, mode == 6 ? post_plain.data() : nullptr, true, host::make_tw<W>(n_inv, q));
+        return 0;
+    }
     if (mode == 0 || mode == 3) {
         e.spectrum_forward((const W *)a, mode == 3 ? (W *)out : spec.data(), batch);
         if (mode == 0) e.spectrum_inverse(spec.data(), (W *)out, batch, post_plain.data());

@@ -166,3 +166,22 @@ def test_emulated_transform_domain_kernels(wb, logn, logr, ppc, red, tag, co):
     assert spec.max() < q                                                                                   # canonical
     assert sorted(spec.tolist()) == sorted(O.forward_negacyclic([int(v) for v in a[0]], psi, q))            # a permutation of ntt(twist(a))
     assert emu.lib().emu_range_violations() == 0
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,red,tag", SPEC)
+def test_emulated_natural_order_transforms_on_the_fused_passes(wb, logn, logr, ppc, red, tag, co):
+    # tntt_forward / tntt_inverse for the fused sizes: Cooley-Tukey passes + permuted store, permuted load + DIT
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    omega = psi * psi % q
+    rng = np.random.default_rng(logn + wb)
+    x = rng.integers(0, q, size=(ppc + 1, n), dtype=np.uint64)
+    x[0] = q - 1
+    fwd = emu.spectrum(wb, logn, logr, ppc, red, x, x, q, psi, 5).astype(np.uint64)
+    assert (fwd == co.cg_ntt(x, omega, q)).all()                                               # cg_ntt
+    assert (emu.spectrum(wb, logn, logr, ppc, red, x, x, q, psi, 7).astype(np.uint64) == co.cg_intt(x, omega, q)).all()   # cg_intt
+    assert (emu.spectrum(wb, logn, logr, ppc, red, fwd, fwd, q, psi, 7).astype(np.uint64) == x).all()
+    tw = emu.spectrum(wb, logn, logr, ppc, red, x[:1], x[:1], q, psi, 4).astype(np.uint64)
+    assert tw[0].tolist() == O.forward_negacyclic([int(v) for v in x[0]], psi, q)              # ntt(twist(a)), natural order
+    assert (emu.spectrum(wb, logn, logr, ppc, red, tw, tw, q, psi, 6).astype(np.uint64) == x[:1]).all()
+    assert emu.lib().emu_range_violations() == 0

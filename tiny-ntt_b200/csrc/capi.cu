@@ -81,12 +81,13 @@ struct tntt_plan {
     void *fwd_pyr = nullptr, *inv_pyr = nullptr, *post_mont = nullptr;  // fused polymul
     void *fwd_last[kMaxLogR + 1] = {};                                 // per LOGR
     void *cyc_fwd_pyr = nullptr;                                       // DIT pyramid of omega (cg_ntt)
+    void *cyc_ct_pyr = nullptr, *cyc_ct_last[kMaxLogR + 1] = {};       // cyclic Cooley-Tukey pyramid of omega (+ transposed last pass)
     void *pre_twist = nullptr, *post_untwist = nullptr;                // psi^i ; psi^-i N^-1
     void *omega_pow = nullptr, *omega_inv_pow = nullptr;               // plain W[n]: literal CG stages
     Tw<uint64_t> one_tw{}, ninv_tw{};
     // first MAX_R entries of the pyramids, passed by value in the kernel parameters
-    Tw<uint32_t> head32[3][MAX_R] = {};   // [0] fwd_pyr, [1] inv_pyr, [2] cyc_fwd_pyr
-    Tw<uint64_t> head64[3][MAX_R] = {};
+    Tw<uint32_t> head32[4][MAX_R] = {};   // [0] fwd_pyr, [1] inv_pyr, [2] cyc_fwd_pyr, [3] cyc_ct_pyr
+    Tw<uint64_t> head64[4][MAX_R] = {};
     const TransformVariant *xform = nullptr;
     const SpectrumVariant *spectrum = nullptr;
     // host pipeline
@@ -118,6 +119,15 @@ template <typename W> int build_tables(tntt_plan *p) {
         CUDA_TRY(upload(ci, &p->inv_pyr));
         keep_head(cf, 2);
         keep_head(ci, 1);
+        // cyclic Cooley-Tukey tables for the shapes of spectrum.cu (natural-order cg_ntt without a bit-reversal pass)
+        int sc = 0;
+        const SpectrumVariant *sv = spectrum_variants(&sc);
+        for (int i = 0; i < sc; ++i)
+            if (sv[i].word_bytes == (int)sizeof(W) && sv[i].logn == logn && !p->cyc_ct_last[sv[i].logr]) {
+                const std::vector<Tw<W>> ct = host::fwd_pyramid_cyclic<W>(p->info.omega, n, q);
+                if (!p->cyc_ct_pyr) { CUDA_TRY(upload(ct, &p->cyc_ct_pyr)); keep_head(ct, 3); }
+                CUDA_TRY(upload(host::fwd_last_table<W>(ct, logn, sv[i].logr), &p->cyc_ct_last[sv[i].logr]));
+            }
     }
     {   // natural power tables for the literal constant-geometry stages (any omega)
         std::vector<uint64_t> f = host::powers(p->info.omega, n, q), b = host::powers(p->info.omega_inv, n, q);
@@ -248,11 +258,11 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
                 break;
             }
     }
-    if (I.has_psi) {
+    if (I.omega_is_primitive) {
         int c = 0;
         const SpectrumVariant *sv = spectrum_variants(&c);
         for (int i = 0; i < c; ++i)
-            if (sv[i].word_bytes == I.word_bytes && sv[i].logn == (int)I.logn && sv[i].red == I.lazy_reduce && p->fwd_last[sv[i].logr]) {
+            if (sv[i].word_bytes == I.word_bytes && sv[i].logn == (int)I.logn && sv[i].red == I.lazy_reduce && p->cyc_ct_last[sv[i].logr]) {
                 if (sv[i].red && !host::lazy_pass_ok<uint64_t>(q, sv[i].logr)) continue;
                 cudaError_t e = sv[i].prepare();
                 if (e != cudaSuccess) { tntt_plan_destroy(p); return fail(TNTT_CUDA_ERROR, "prepare %s: %s", sv[i].name, cudaGetErrorString(e)); }
@@ -260,7 +270,7 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
                 break;
             }
     }
-    I.spectrum = p->spectrum ? 1 : 0;
+    I.spectrum = (p->spectrum && I.has_psi && p->fwd_last[p->spectrum->logr]) ? 1 : 0;
     const std::vector<PolymulVariant> &vs = all_variants();
     for (size_t i = 0; i < vs.size(); ++i)
         if (tntt_variant_matches(p, (int)i)) {
@@ -321,6 +331,29 @@ int fast_transform(const tntt_plan *p, const void *in, void *out, size_t batch, 
     return TNTT_OK;
 }
 
+// natural-order transforms on the fused kernel's passes (canonical inputs): forward = Cooley-Tukey high bit first +
+// permuted store, inverse = permuted load + decimation in time; twist = merged-psi tables / psi^-i N^-1 store table
+template <typename W>
+int natural_transform(const tntt_plan *p, const void *in, void *out, size_t batch, bool inverse, int flags, cudaStream_t st) {
+    const SpectrumVariant &v = *p->spectrum;
+    const bool twist = (flags & TNTT_TWIST) != 0;
+    PolymulTables<W> tb{};
+    tb.inv.pyr = (const Tw<W> *)p->inv_pyr;
+    const int hf = twist ? 0 : 3;
+    tb.fwd_pyr = (const Tw<W> *)(twist ? p->fwd_pyr : p->cyc_ct_pyr);
+    tb.fwd_last = (const Tw<W> *)(twist ? p->fwd_last[v.logr] : p->cyc_ct_last[v.logr]);
+    if constexpr (sizeof(W) == 4) { memcpy(tb.fwd_head, p->head32[hf], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head32[1], sizeof tb.inv.head); }
+    else { memcpy(tb.fwd_head, p->head64[hf], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head64[1], sizeof tb.inv.head); }
+    cudaError_t e;
+    if (!inverse) e = v.forward_natural(in, out, batch, &tb, p->mod(), st);
+    else {
+        const Tw<W> ninv = host::make_tw<W>(p->info.n_inv, p->info.q);
+        e = v.inverse_natural(in, out, batch, &tb, twist ? p->post_untwist : nullptr, ninv.w, ninv.wp, p->mod(), st);
+    }
+    if (e != cudaSuccess) return fail(TNTT_CUDA_ERROR, "%s: %s", v.name, cudaGetErrorString(e));
+    return TNTT_OK;
+}
+
 int transform(const tntt_plan *p, const void *in, void *out, size_t batch, bool inverse, int flags, void *stream) {
     int rc = check_io(p, in, out, batch);
     if (rc) return rc;
@@ -329,6 +362,9 @@ int transform(const tntt_plan *p, const void *in, void *out, size_t batch, bool 
     if (batch == 0) return TNTT_OK;
     DeviceSetter ds(p->info.device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->spectrum && !(flags & TNTT_REDUCE_INPUT) && (!(flags & TNTT_TWIST) || p->info.spectrum))
+        return p->info.word_bytes == 4 ? natural_transform<uint32_t>(p, in, out, batch, inverse, flags, st)
+                                       : natural_transform<uint64_t>(p, in, out, batch, inverse, flags, st);
     if (p->xform) return p->info.word_bytes == 4 ? fast_transform<uint32_t>(p, in, out, batch, inverse, flags, st)
                                                 : fast_transform<uint64_t>(p, in, out, batch, inverse, flags, st);
     return generic_transform(p, in, out, batch, inverse, flags, st);
@@ -370,7 +406,7 @@ template <typename W> int spectrum_op(const tntt_plan *p, int op, const void *a,
 int spectrum_entry(const tntt_plan *p, int op, const void *a, const void *b, void *out, size_t batch, size_t b_rows, void *stream) {
     int rc = check_io(p, a, op == 2 ? b : a, batch);
     if (rc) return rc;
-    if (!p->spectrum) return fail(TNTT_UNSUPPORTED_N, "no transform-domain kernels for this plan (needs psi and a fused size: n in {256, 1024, 4096})");
+    if (!p->info.spectrum) return fail(TNTT_UNSUPPORTED_N, "no transform-domain kernels for this plan (needs psi and a fused size: n in {256, 1024, 4096})");
     if (batch == 0) return TNTT_OK;
     if (!out || ((uintptr_t)out & 15)) return fail(TNTT_BAD_ARG, "output must be a 16-byte aligned device pointer");
     if (op == 2 && b_rows != 1 && b_rows != batch) return fail(TNTT_BAD_ARG, "b_rows must be 1 (shared spectrum) or the batch size");
@@ -467,6 +503,8 @@ int tntt_plan_destroy(tntt_plan *p) {
     void *bufs[] = {p->fwd_pyr, p->inv_pyr, p->post_mont, p->cyc_fwd_pyr, p->pre_twist, p->post_untwist, p->omega_pow, p->omega_inv_pow};
     for (void *b : bufs) if (b) cudaFree(b);
     for (void *b : p->fwd_last) if (b) cudaFree(b);
+    if (p->cyc_ct_pyr) cudaFree(p->cyc_ct_pyr);
+    for (void *t : p->cyc_ct_last) if (t) cudaFree(t);
     for (int s = 0; s < tntt_plan::kSlots; ++s) {
         for (void *b : p->pipe_buf[s]) if (b) cudaFree(b);
         if (p->pipe_stream[s]) cudaStreamDestroy(p->pipe_stream[s]);

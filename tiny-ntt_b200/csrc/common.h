@@ -41,6 +41,10 @@ struct SpectrumVariant {
     cudaError_t (*polymul)(const void *a, const void *bspec, void *c, size_t batch, size_t b_stride, const void *tables,
                            const void *mod, cudaStream_t st);
     cudaError_t (*prepare)();
+    // natural-order transforms built from the same passes (tables decide merged-psi or cyclic)
+    cudaError_t (*forward_natural)(const void *in, void *out, size_t batch, const void *tables, const void *mod, cudaStream_t st);
+    cudaError_t (*inverse_natural)(const void *in, void *out, size_t batch, const void *tables, const void *post, uint64_t uw,
+                                   uint64_t uwp, const void *mod, cudaStream_t st);   // post == nullptr: scale by {uw, uwp}
 };
 const SpectrumVariant *spectrum_variants(int *count);
 

@@ -29,6 +29,11 @@ namespace tntt {
 
 TNTT_CX int cmax(int a, int b) { return a > b ? a : b; }
 TNTT_CX int cmin(int a, int b) { return a < b ? a : b; }
+TNTT_CX int cbitrev(int v, int bits) {   // compile-time bit reversal (register indices)
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+}
 
 // Geometry of one kernel variant: W word, N = 2^LOGN coefficients, R = 2^LOGR per thread,
 // PPC polynomials per CTA, NA operands transformed side by side (sharing twiddle loads).
@@ -627,7 +632,12 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
 //   spectrum_inverse_kernel  = its inverse half                            (untwist(cg_intt(.)), cg_ntt.py:90-92)
 //   polymul_spectrum_kernel  = polymul_kernel with b's transform replaced by a load (b may be one shared row)
 // ---------------------------------------------------------------------------------------------
-template <class C, bool RED, int MINB>
+// NATURAL = true turns the two kernels into natural-order transforms (cg_ntt / cg_intt and their twisted forms,
+// new_reference/cg_ntt.py:29-75): position p = t*R + k of the bit-reversed-order spectrum is natural index
+// bitrev(p) = (bitrev_R(k) << log2 P) | bitrev_P(t).  For P <= 32 a warp's permuted accesses still cover whole
+// contiguous segments, so the permutation costs nothing; otherwise it goes through the tile once.  The tables
+// decide the transform: merged-psi pyramid = ntt(twist(.)), cyclic pyramid (host::fwd_pyramid_cyclic) = cg_ntt.
+template <class C, bool RED, int MINB, bool NATURAL = false>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
                         const __grid_constant__ PolymulTables<typename C::W> tb,
@@ -643,17 +653,35 @@ spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__r
     row_load<C>(x[0], in + off, tid, active);
     forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
 #pragma unroll
-    for (int k = 0; k < C::R; ++k) {
-        const W v = csub(shoup_mul(x[0][k], (W)1, mod.one_p, mod.nq), mod.q);   // any word -> [0, q)
-        if (active) st_stream(out + off + (k << C::LOGP) + tid, v);
+    for (int k = 0; k < C::R; ++k) x[0][k] = csub(shoup_mul(x[0][k], (W)1, mod.one_p, mod.nq), mod.q);   // any word -> [0, q)
+    if constexpr (!NATURAL) {
+#pragma unroll
+        for (int k = 0; k < C::R; ++k)
+            if (active) st_stream(out + off + (k << C::LOGP) + tid, x[0][k]);
+    } else if constexpr (C::P <= 32) {
+        const int bt = bitrev_n(tid, C::LOGP);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k)
+            if (active) st_stream(out + off + (cbitrev(k, C::LOGR) << C::LOGP) + bt, x[0][k]);
+    } else {
+        const int bt = bitrev_n(tid, C::LOGP);
+        tile_sync<C>();
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) tile[C::spos(pl * C::N + ((cbitrev(k, C::LOGR) << C::LOGP) | bt))] = x[0][k];
+        tile_sync<C>();
+#pragma unroll
+        for (int k = 0; k < C::R; ++k)
+            if (active) st_stream(out + off + (k << C::LOGP) + tid, tile[C::spos(pl * C::N + (k << C::LOGP) + tid)]);
     }
 }
 
-template <class C, bool RED, int MINB>
+// TABLE: the store multiplies by the per-coefficient table `post` (psi^-i N^-1: twisted inverse) or, TABLE = false,
+// by the one factor `post_uniform` (N^-1: cg_intt)
+template <class C, bool RED, int MINB, bool NATURAL = false, bool TABLE = true>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
                         const __grid_constant__ DitTables<typename C::W> inv, const Tw<typename C::W> *__restrict__ post,
-                        const __grid_constant__ Mod<typename C::W> mod) {
+                        const Tw<typename C::W> post_uniform, const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W *tile = reinterpret_cast<W *>(smem_raw);
@@ -662,9 +690,24 @@ spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__r
     const bool active = poly < batch;
     const size_t off = active ? poly * C::N : 0;
     W x[C::R];
-    row_load<C>(x, in + off, tid, active);                      // spectrum order == the coalesced row pattern
-    dit_all<C, RED, 1, false, C::PREFETCH>(x, tile, pl, tid, inv, post, mod);   // canonical input: below one unit
-    row_store_scaled<C, 1>(x, out + off, tid, active, post, Tw<W>{0, 0}, mod);
+    if constexpr (!NATURAL) {
+        row_load<C>(x, in + off, tid, active);                  // spectrum order == the coalesced row pattern
+    } else if constexpr (C::P <= 32) {
+        const int bt = bitrev_n(tid, C::LOGP);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) x[k] = active ? ld_stream(in + off + (cbitrev(k, C::LOGR) << C::LOGP) + bt) : (W)0;
+    } else {
+        // the tile holds the row in natural order: coalesced write, permuted read (the mirror image of the forward store)
+        const int bt = bitrev_n(tid, C::LOGP);
+        row_load<C>(x, in + off, tid, active);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) tile[C::spos(pl * C::N + (k << C::LOGP) + tid)] = x[k];
+        tile_sync<C>();
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) x[k] = tile[C::spos(pl * C::N + ((cbitrev(k, C::LOGR) << C::LOGP) | bt))];
+    }
+    dit_all<C, RED, 1, false, C::PREFETCH>(x, tile, pl, tid, inv, TABLE ? post : nullptr, mod);   // canonical input: below one unit
+    row_store_scaled<C, TABLE ? 1 : 0>(x, out + off, tid, active, post, post_uniform, mod);
 }
 
 // b_stride = N: one spectrum per row; b_stride = 0: one spectrum shared by the whole batch

@@ -18,7 +18,26 @@ template <class C, bool RED, int MINB> struct SpectrumInst {
                                cudaStream_t st) {
         spectrum_inverse_kernel<C, RED, MINB><<<ctas(batch), C::THREADS, SMEM, st>>>(
             static_cast<const W *>(in), static_cast<W *>(out), batch, static_cast<const PolymulTables<W> *>(tables)->inv,
-            static_cast<const Tw<W> *>(post), *static_cast<const Mod<W> *>(mod));
+            static_cast<const Tw<W> *>(post), Tw<W>{0, 0}, *static_cast<const Mod<W> *>(mod));
+        return cudaGetLastError();
+    }
+    static cudaError_t forward_natural(const void *in, void *out, size_t batch, const void *tables, const void *mod, cudaStream_t st) {
+        spectrum_forward_kernel<C, RED, MINB, true><<<ctas(batch), C::THREADS, SMEM, st>>>(
+            static_cast<const W *>(in), static_cast<W *>(out), batch, *static_cast<const PolymulTables<W> *>(tables),
+            *static_cast<const Mod<W> *>(mod));
+        return cudaGetLastError();
+    }
+    static cudaError_t inverse_natural(const void *in, void *out, size_t batch, const void *tables, const void *post, uint64_t uw,
+                                       uint64_t uwp, const void *mod, cudaStream_t st) {
+        const DitTables<W> &inv = static_cast<const PolymulTables<W> *>(tables)->inv;
+        if (post)
+            spectrum_inverse_kernel<C, RED, MINB, true, true><<<ctas(batch), C::THREADS, SMEM, st>>>(
+                static_cast<const W *>(in), static_cast<W *>(out), batch, inv, static_cast<const Tw<W> *>(post), Tw<W>{0, 0},
+                *static_cast<const Mod<W> *>(mod));
+        else
+            spectrum_inverse_kernel<C, RED, MINB, true, false><<<ctas(batch), C::THREADS, SMEM, st>>>(
+                static_cast<const W *>(in), static_cast<W *>(out), batch, inv, nullptr, Tw<W>{(W)uw, (W)uwp},
+                *static_cast<const Mod<W> *>(mod));
         return cudaGetLastError();
     }
     static cudaError_t polymul(const void *a, const void *bspec, void *c, size_t batch, size_t b_stride, const void *tables,
@@ -32,6 +51,9 @@ template <class C, bool RED, int MINB> struct SpectrumInst {
         cudaError_t e = cudaFuncSetAttribute(spectrum_forward_kernel<C, RED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_inverse_kernel<C, RED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(polymul_spectrum_kernel<C, RED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_forward_kernel<C, RED, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_inverse_kernel<C, RED, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_inverse_kernel<C, RED, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         return e;
     }
 };
@@ -42,7 +64,9 @@ template <class C, bool RED, int MINB> struct SpectrumInst {
             &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::forward,                                   \
             &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::inverse,                                   \
             &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::polymul,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::prepare                                    \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::prepare,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::forward_natural,                           \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::inverse_natural                            \
     }
 
 // one shape per (word, N, reduction mode): the spectrum order is part of the plan, not of a kernel variant

@@ -112,6 +112,17 @@ template <typename W> inline std::vector<Tw<W>> fwd_pyramid(uint64_t psi, uint32
     return t;
 }
 
+// cyclic Cooley-Tukey twiddles (natural order in, bit-reversed order out): entry m + i, m = 2^s blocks, is
+// omega^(bitrev(i, s) * n / 2m) -- the per-block twiddle of cg_ntt's transform when it is run high index bit
+// first.  Same indexing as fwd_pyramid, so the same kernels run either transform.
+template <typename W> inline std::vector<Tw<W>> fwd_pyramid_cyclic(uint64_t omega, uint32_t n, uint64_t q) {
+    const std::vector<uint64_t> pw = powers(omega, n, q);
+    std::vector<Tw<W>> t(n > 1 ? n : 2, make_tw<W>(1 % q, q));
+    for (uint32_t m = 1, s = 0; m < n; m <<= 1, ++s)
+        for (uint32_t i = 0; i < m; ++i) t[m + i] = make_tw<W>(pw[(size_t)bitrev(i, (int)s) * (n / (2 * m))], q);
+    return t;
+}
+
 // the last forward pass reads fwd_pyramid transposed: [slot][tid], see fwd_pass() in kernels.cuh
 template <typename W>
 inline std::vector<Tw<W>> fwd_last_table(const std::vector<Tw<W>> &pyr, int logn, int logr) {
