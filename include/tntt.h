@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TNTT_VERSION 100 /* 0.1.0 */
+#define TNTT_VERSION 101 /* 0.1.1 */
 
 enum tntt_status {
     TNTT_OK = 0,
@@ -165,6 +165,8 @@ int tntt_microbench(int device, int kind, double *ops_per_second);
 
 const char *tntt_last_error(void);
 int tntt_version(void);
+/* sizeof(tntt_plan_info) as the library was built: lets a binding check its mirror of the struct at load time */
+size_t tntt_plan_info_size(void);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/tntt.h but not exported"
     assert sorted(tntt.SYMBOLS) == declared, "python binding and header disagree"
-    assert tntt.lib().tntt_version() == 100
+    assert tntt.lib().tntt_version() == 101
     # nothing but the C ABI leaks out of the shared object
     out = subprocess.check_output(["nm", "-D", "--defined-only", tntt.LIB_PATH], text=True)
     exported = sorted(line.split()[-1] for line in out.splitlines() if " T " in line)

@@ -437,6 +437,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 
 int tntt_version(void) { return TNTT_VERSION; }
+size_t tntt_plan_info_size(void) { return sizeof(tntt_plan_info); }
 const char *tntt_last_error(void) { return g_err.c_str(); }
 
 int tntt_plan_create(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t root, int root_is_psi) {

@@ -20,7 +20,7 @@ SYMBOLS = (
     "tntt_cg_stage", "tntt_bit_reverse", "tntt_scale", "tntt_reduce", "tntt_butterfly_batch", "tntt_variant_count",
     "tntt_variant_describe", "tntt_variant_matches", "tntt_polymul_variant", "tntt_plan_set_default_variant",
     "tntt_microbench", "tntt_last_error", "tntt_version",
-    "tntt_spectrum_forward", "tntt_spectrum_inverse", "tntt_polymul_spectrum",
+    "tntt_spectrum_forward", "tntt_spectrum_inverse", "tntt_polymul_spectrum", "tntt_plan_info_size",
 )
 
 
@@ -82,6 +82,10 @@ def lib() -> C.CDLL:
     L.tntt_microbench.argtypes = [i, i, C.POINTER(C.c_double)]
     L.tntt_last_error.restype = C.c_char_p
     L.tntt_version.restype = i
+    L.tntt_plan_info_size.restype = sz
+    if L.tntt_plan_info_size() != C.sizeof(PlanInfo):
+        raise RuntimeError(f"libtntt.so was built with a different tntt_plan_info ({L.tntt_plan_info_size()} bytes) than "
+                           f"this binding mirrors ({C.sizeof(PlanInfo)} bytes): rebuild the library")
     _lib = L
     return L
 
