@@ -185,3 +185,51 @@ def test_transform_domain_api(tag):
     assert small.spectrum == 0
     with pytest.raises(tntt.TnttError):
         tntt.forward_spectrum(small, torch.zeros((1, 64), dtype=torch.int32, device="cuda"))
+
+
+def test_entry_points_are_cuda_graph_capturable():
+    # every fused-size entry point only enqueues kernels on the caller's stream (no allocation, no synchronisation),
+    # so a launch-bound loop of small products can be captured once and replayed as a CUDA graph
+    import tntt
+
+    p = O.PARAMS["n4096_60"]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    plan = tntt.get_plan(n, q, psi, True)
+    co = COracle()
+    rng = np.random.default_rng(9)
+    rows = 4                                            # cluster-kernel territory
+    a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    ta = torch.from_numpy(a.view(np.int64)).cuda()
+    tb = torch.from_numpy(b.view(np.int64)).cuda()
+    c = torch.empty_like(ta)
+    s = torch.empty_like(ta)
+    r = torch.empty_like(ta)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm-up outside capture, on the capture stream
+        tntt.polymul(plan, ta, tb, out=c)
+        tntt.forward_spectrum(plan, tb, out=s)
+        tntt.polymul_spectrum(plan, ta, s, out=r)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    c.zero_()
+    r.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        tntt.polymul(plan, ta, tb, out=c)
+        tntt.forward_spectrum(plan, tb, out=s)
+        tntt.polymul_spectrum(plan, ta, s, out=r)
+        tntt.inverse(plan, tntt.forward(plan, ta), out=s)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    assert (c.cpu().numpy().view(np.uint64) == want).all()
+    assert (r.cpu().numpy().view(np.uint64) == want).all()
+    assert torch.equal(s, ta)
+    # new inputs, same graph
+    ta.copy_(tb)
+    g.replay()
+    torch.cuda.synchronize()
+    assert (c.cpu().numpy().view(np.uint64) == co.nwc_poly_mult(b, b, psi, q, threads=4)).all()
