@@ -652,22 +652,25 @@ spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__r
     W x[1][C::R];
     row_load<C>(x[0], in + off, tid, active);
     forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
-#pragma unroll
-    for (int k = 0; k < C::R; ++k) x[0][k] = csub(shoup_mul(x[0][k], (W)1, mod.one_p, mod.nq), mod.q);   // any word -> [0, q)
+    auto canon = [&](W v) { return csub(shoup_mul(v, (W)1, mod.one_p, mod.nq), mod.q); };   // any word -> [0, q)
     if constexpr (!NATURAL) {
 #pragma unroll
-        for (int k = 0; k < C::R; ++k)
-            if (active) st_stream(out + off + (k << C::LOGP) + tid, x[0][k]);
+        for (int k = 0; k < C::R; ++k) {
+            const W v = canon(x[0][k]);
+            if (active) st_stream(out + off + (k << C::LOGP) + tid, v);
+        }
     } else if constexpr (C::P <= 32) {
         const int bt = bitrev_n(tid, C::LOGP);
 #pragma unroll
-        for (int k = 0; k < C::R; ++k)
-            if (active) st_stream(out + off + (cbitrev(k, C::LOGR) << C::LOGP) + bt, x[0][k]);
+        for (int k = 0; k < C::R; ++k) {
+            const W v = canon(x[0][k]);
+            if (active) st_stream(out + off + (cbitrev(k, C::LOGR) << C::LOGP) + bt, v);
+        }
     } else {
         const int bt = bitrev_n(tid, C::LOGP);
         tile_sync<C>();
 #pragma unroll
-        for (int k = 0; k < C::R; ++k) tile[C::spos(pl * C::N + ((cbitrev(k, C::LOGR) << C::LOGP) | bt))] = x[0][k];
+        for (int k = 0; k < C::R; ++k) tile[C::spos(pl * C::N + ((cbitrev(k, C::LOGR) << C::LOGP) | bt))] = canon(x[0][k]);
         tile_sync<C>();
 #pragma unroll
         for (int k = 0; k < C::R; ++k)
