@@ -25,6 +25,14 @@
 #pragma once
 #include "modarith.cuh"
 
+// how many twiddles (TNTT_TG) / store-table entries (TNTT_POST_GROUP) are fetched ahead of their use
+#ifndef TNTT_TG
+#define TNTT_TG 4
+#endif
+#ifndef TNTT_POST_GROUP
+#define TNTT_POST_GROUP 4
+#endif
+
 namespace tntt {
 
 TNTT_CX int cmax(int a, int b) { return a > b ? a : b; }
@@ -195,7 +203,7 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
         for (int a = 0; a < NA; ++a) reduce_top_x<C, kb>(x[a], mod);
     }
     // twiddles are fetched TG at a time, ahead of their butterflies, so that their latencies overlap
-    constexpr int TG = NG < 4 ? NG : 4;
+    constexpr int TG = NG < TNTT_TG ? NG : TNTT_TG;
 #pragma unroll
     for (int g0 = 0; g0 < NG; g0 += TG) {
         Tw<W> tw[TG];
@@ -307,7 +315,7 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
     } else {
     if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
         reduce_top_x<C, kb>(x, mod);
-    constexpr int TG = NJ < 4 ? NJ : 4;
+    constexpr int TG = NJ < TNTT_TG ? NJ : TNTT_TG;
 #pragma unroll
     for (int j0 = 0; j0 < NJ; j0 += TG) {
         Tw<W> tw[TG];
@@ -390,7 +398,7 @@ template <class C> TNTT_HD void row_load(typename C::W (&x)[C::R], const typenam
 // final multiply (psi^-i N^-1 ...) + canonical reduction + coalesced store.
 // TABLE: 1 = per-coefficient table `post` (loaded GROUP entries at a time so that their L2 latencies
 // overlap instead of one exposed load per coefficient), 0 = one uniform factor, -1 = decided at run time.
-template <class C, int TABLE = -1, int GROUP_ = 4>
+template <class C, int TABLE = -1, int GROUP_ = TNTT_POST_GROUP>
 TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row, int tid, bool active,
                               const Tw<typename C::W> *post, const Tw<typename C::W> &post_uniform,
                               const Mod<typename C::W> &mod) {
