@@ -326,6 +326,15 @@ int emu_spectrum(int word_bytes, int logn, int logr, int ppc, int red, const voi
     SPEC_CASE(8, uint64_t, 10, 4, 4, 1)
     SPEC_CASE(8, uint64_t, 12, 4, 1, 0)
     SPEC_CASE(8, uint64_t, 12, 4, 1, 1)
+    SPEC_CASE(4, uint32_t, 9, 5, 16, 0)
+    SPEC_CASE(4, uint32_t, 11, 4, 2, 0)
+    SPEC_CASE(4, uint32_t, 13, 5, 1, 0)
+    SPEC_CASE(8, uint64_t, 9, 4, 8, 0)
+    SPEC_CASE(8, uint64_t, 9, 4, 8, 1)
+    SPEC_CASE(8, uint64_t, 11, 4, 2, 0)
+    SPEC_CASE(8, uint64_t, 11, 4, 2, 1)
+    SPEC_CASE(8, uint64_t, 13, 4, 1, 0)
+    SPEC_CASE(8, uint64_t, 13, 4, 1, 1)
     return -1;
 }
 
@@ -354,6 +363,16 @@ int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, co
     POLY_CASE(8, uint64_t, 12, 4, 1, 2, 1)
     POLY_CASE(8, uint64_t, 12, 3, 1, 1, 1)
     POLY_CASE(8, uint64_t, 12, 3, 1, 2, 1)
+    // N = 512, 2048, 8192
+    POLY_CASE(4, uint32_t, 9, 5, 16, 2, 0)
+    POLY_CASE(4, uint32_t, 11, 4, 2, 2, 0)
+    POLY_CASE(4, uint32_t, 13, 5, 1, 2, 0)
+    POLY_CASE(8, uint64_t, 9, 4, 8, 1, 0)
+    POLY_CASE(8, uint64_t, 9, 4, 8, 1, 1)
+    POLY_CASE(8, uint64_t, 11, 4, 2, 1, 0)
+    POLY_CASE(8, uint64_t, 11, 4, 2, 1, 1)
+    POLY_CASE(8, uint64_t, 13, 4, 1, 1, 0)
+    POLY_CASE(8, uint64_t, 13, 4, 1, 1, 1)
     return -1;
 }
 

@@ -233,3 +233,40 @@ def test_entry_points_are_cuda_graph_capturable():
     g.replay()
     torch.cuda.synchronize()
     assert (c.cpu().numpy().view(np.uint64) == co.nwc_poly_mult(b, b, psi, q, threads=4)).all()
+
+
+Q60 = (1 << 60) - (1 << 14) + 1
+OTHER_RINGS = [(512, 8380417, 1718063), (2048, 8380417, 7901702), (8192, 67043329, 8157893),
+               (512, Q60, 984081769261068913), (2048, Q60, 644283108363935541), (8192, Q60, 527760526715669589)]
+
+
+@pytest.mark.parametrize("n,q,psi", OTHER_RINGS)
+def test_fused_kernels_for_other_ring_sizes(n, q, psi):
+    # N = 512, 2048, 8192 (the sizes between and above the reference's three) have fused, transform-domain and
+    # natural-order kernels too; everything against the oracle
+    import tntt
+
+    plan = tntt.get_plan(n, q, psi, True)
+    assert plan.fused == 1 and plan.spectrum == 1
+    co = COracle()
+    omega = psi * psi % q
+    npdt = np.uint32 if plan.word_bytes == 4 else np.uint64
+    sdt = np.int32 if plan.word_bytes == 4 else np.int64
+    rng = np.random.default_rng(n)
+    rows = 19
+    a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    dev = lambda v: torch.from_numpy(np.ascontiguousarray(v).astype(npdt).view(sdt)).cuda()      # noqa: E731
+    host = lambda t: t.cpu().numpy().view(npdt).astype(np.uint64)                                # noqa: E731
+    ta, tb = dev(a), dev(b)
+    want = co.nwc_poly_mult(a, b, psi, q, threads=8)
+    for v, desc in plan.variants():
+        assert (host(tntt.polymul(plan, ta, tb, variant=v)) == want).all(), desc
+    assert (host(tntt.polymul(plan, ta, tb)) == want).all()
+    sb = tntt.forward_spectrum(plan, tb)
+    assert (host(tntt.polymul_spectrum(plan, ta, sb)) == want).all()
+    assert (host(tntt.inverse_spectrum(plan, tntt.pointwise(plan, tntt.forward_spectrum(plan, ta), sb))) == want).all()
+    assert (host(tntt.forward(plan, ta)) == co.cg_ntt(a, omega, q)).all()
+    assert (host(tntt.inverse(plan, ta)) == co.cg_intt(a, omega, q)).all()
+    assert torch.equal(tntt.inverse(plan, tntt.forward(plan, ta, twist=True), twist=True), ta)

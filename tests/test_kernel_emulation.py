@@ -185,3 +185,32 @@ def test_emulated_natural_order_transforms_on_the_fused_passes(wb, logn, logr, p
     assert tw[0].tolist() == O.forward_negacyclic([int(v) for v in x[0]], psi, q)              # ntt(twist(a)), natural order
     assert (emu.spectrum(wb, logn, logr, ppc, red, tw, tw, q, psi, 6).astype(np.uint64) == x[:1]).all()
     assert emu.lib().emu_range_violations() == 0
+
+
+# sizes next to the reference's three (other NTT-friendly rings): (word, logn, logr, ppc, na, red, q, psi)
+Q60 = (1 << 60) - (1 << 14) + 1
+EXTRA_SIZES = [
+    (4, 9, 5, 16, 2, 0, 8380417, 1718063), (4, 11, 4, 2, 2, 0, 8380417, 7901702), (4, 13, 5, 1, 2, 0, 67043329, 8157893),
+    (8, 9, 4, 8, 1, 0, 8380417, 1718063), (8, 9, 4, 8, 1, 1, Q60, 984081769261068913),
+    (8, 11, 4, 2, 1, 0, 8380417, 7901702), (8, 11, 4, 2, 1, 1, Q60, 644283108363935541),
+    (8, 13, 4, 1, 1, 0, 67043329, 8157893), (8, 13, 4, 1, 1, 1, Q60, 527760526715669589),
+]
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,na,red,q,psi", EXTRA_SIZES)
+def test_emulated_kernels_at_other_sizes(wb, logn, logr, ppc, na, red, q, psi, co):
+    n = 1 << logn
+    assert pow(psi, n, q) == q - 1
+    omega = psi * psi % q
+    rng = np.random.default_rng(logn)
+    batch = ppc + 1
+    a = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    assert (emu.polymul(wb, logn, logr, ppc, na, red, a, b, q, psi).astype(np.uint64) == want).all()
+    assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 1).astype(np.uint64) == want).all()
+    assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 0).astype(np.uint64) == a).all()
+    assert (emu.spectrum(wb, logn, logr, ppc, red, a, a, q, psi, 5).astype(np.uint64) == co.cg_ntt(a, omega, q)).all()
+    assert (emu.spectrum(wb, logn, logr, ppc, red, a, a, q, psi, 7).astype(np.uint64) == co.cg_intt(a, omega, q)).all()
+    assert emu.lib().emu_range_violations() == 0

@@ -406,7 +406,7 @@ template <typename W> int spectrum_op(const tntt_plan *p, int op, const void *a,
 int spectrum_entry(const tntt_plan *p, int op, const void *a, const void *b, void *out, size_t batch, size_t b_rows, void *stream) {
     int rc = check_io(p, a, op == 2 ? b : a, batch);
     if (rc) return rc;
-    if (!p->info.spectrum) return fail(TNTT_UNSUPPORTED_N, "no transform-domain kernels for this plan (needs psi and a fused size: n in {256, 1024, 4096})");
+    if (!p->info.spectrum) return fail(TNTT_UNSUPPORTED_N, "no transform-domain kernels for this plan (needs psi and a fused size: n in {256, 512, 1024, 2048, 4096, 8192})");
     if (batch == 0) return TNTT_OK;
     if (!out || ((uintptr_t)out & 15)) return fail(TNTT_BAD_ARG, "output must be a 16-byte aligned device pointer");
     if (op == 2 && b_rows != 1 && b_rows != batch) return fail(TNTT_BAD_ARG, "b_rows must be 1 (shared spectrum) or the batch size");

@@ -20,6 +20,10 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 12, 3, 1, 2, 0, 2),
     // small batches: one row per cluster of 4 CTAs, exchanges through distributed shared memory
     TNTT_POLYMUL_CLUSTER(uint32_t, 32, 12, 3, 4, 0),
+    // sizes next to the reference's three (other NTT-friendly rings): N = 512, 2048, 8192
+    TNTT_POLYMUL_VARIANT(uint32_t, 32, 9, 5, 16, 2, 0, 2),
+    TNTT_POLYMUL_VARIANT(uint32_t, 32, 11, 4, 2, 2, 0, 4),
+    TNTT_POLYMUL_VARIANT(uint32_t, 32, 13, 5, 1, 2, 0, 2),
 };
 const PolymulVariant *polymul_variants_u32(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));

@@ -1,4 +1,4 @@
-// Fused negacyclic polymul kernels for uint64 coefficients at the smaller sizes (N = 256, 1024).
+// Fused negacyclic polymul kernels for uint64 coefficients at the sizes other than N = 4096.
 #include "polymul_inst.cuh"
 
 namespace tntt {
@@ -7,6 +7,13 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 8, 4, 16, 1, 1, 2),
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 10, 4, 4, 1, 0, 2),
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 10, 4, 4, 1, 1, 2),
+    // sizes next to the reference's three (other NTT-friendly rings): N = 512, 2048, 8192
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 9, 4, 8, 1, 0, 2),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 9, 4, 8, 1, 1, 2),
+    TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 11, 4, 2, 1, 0, 3, 1),
+    TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 11, 4, 2, 1, 1, 3, 1),
+    TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 13, 4, 1, 1, 0, 1, 1),
+    TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 13, 4, 1, 1, 1, 1, 1),
 };
 const PolymulVariant *polymul_variants_u64b(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));

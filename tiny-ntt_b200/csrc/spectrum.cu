@@ -80,6 +80,16 @@ static const SpectrumVariant kVariants[] = {
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 10, 4, 4, 1, 2),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 12, 4, 1, 0, 2),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 12, 4, 1, 1, 3),
+    // N = 512, 2048, 8192
+    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 9, 5, 16, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 11, 4, 2, 0, 4),
+    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 13, 5, 1, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 9, 4, 8, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 9, 4, 8, 1, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 11, 4, 2, 0, 3),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 11, 4, 2, 1, 3),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 13, 4, 1, 0, 1),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 13, 4, 1, 1, 1),
 };
 const SpectrumVariant *spectrum_variants(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
