@@ -737,8 +737,9 @@ polymul_spectrum_kernel(const typename C::W *__restrict__ a, const typename C::W
     const size_t off = active ? poly * C::N : 0;
     const W *brow = bspec + (active ? poly * b_stride : 0);
     W x[1][C::R], fa[C::R];
-    // b's spectrum is needed one forward transform from now: pull its row towards L2 meanwhile
-    for (int line = tid; line < (int)(C::N * sizeof(W) / 128); line += C::P)
+    // b's spectrum is needed one forward transform from now: pull its row towards L2 meanwhile (a spectrum shared
+    // by the whole batch is hot anyway)
+    for (int line = tid; b_stride != 0 && line < (int)(C::N * sizeof(W) / 128); line += C::P)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(brow) + (size_t)line * 128));
     row_load<C>(x[0], a + off, tid, active);
     forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
