@@ -564,7 +564,13 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W *tile = reinterpret_cast<W *>(smem_raw);
     const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
+#if defined(TNTT_X_PERSISTENT)
+    // what-if: a grid of (SMs x CTAs per SM) persistent CTAs strides over the rows
+    for (size_t blk = blockIdx.x; blk * C::PPC < batch; blk += gridDim.x) {
+    const size_t poly = blk * C::PPC + pl;
+#else
     const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
+#endif
     const bool active = poly < batch;
     const size_t off = active ? poly * C::N : 0;
 #if defined(TNTT_X_EMPTY_KERNEL)
@@ -625,6 +631,9 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     }
     dit_all<C, RED, pointwise_out_bound<C, RED>(), (TMA != 0), C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod, tma, stab);
     row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+#if defined(TNTT_X_PERSISTENT)
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

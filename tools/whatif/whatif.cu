@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../../tiny-ntt_b200/csrc/common.h"
@@ -91,7 +92,12 @@ int main(int argc, char **argv) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kern));
     int bps = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, C::THREADS, smem));
-    auto launch = [&]() { kern<<<(unsigned)rows, C::THREADS, smem>>>(da, db, dc, rows, tb, mod); };
+#ifdef TNTT_X_PERSISTENT
+    const unsigned grid = (unsigned)std::min<size_t>(rows, (size_t)148 * bps);
+#else
+    const unsigned grid = (unsigned)rows;
+#endif
+    auto launch = [&]() { kern<<<grid, C::THREADS, smem>>>(da, db, dc, rows, tb, mod); };
 #endif
     for (int i = 0; i < 3; ++i) launch();
     CK(cudaDeviceSynchronize());
