@@ -71,3 +71,23 @@ def transform(wb, logn, logr, ppc, red, x, q, root, mode, reduce_input=0):
     if rc:
         raise RuntimeError(f"emu_transform rc={rc}")
     return out
+
+
+def largest_friendly_prime(n, ok):
+    """Largest prime q = 1 (mod 2n) below 2^60 for which ok(q) holds (ok is monotone: true below a limit)."""
+    L = lib()
+    lo, hi = 3, (1 << 60) - 1
+    while lo < hi:                                   # largest q with ok(q)
+        mid = (lo + hi + 1) // 2
+        lo, hi = (mid, hi) if ok(mid) else (lo, mid - 1)
+    q = lo - (lo - 1) % (2 * n)                      # largest value = 1 mod 2n not above the limit
+    while not L.emu_is_prime(q):
+        q -= 2 * n
+    return q
+
+
+def largest_modulus_of_path(word_bytes, logn, red):
+    """The largest NTT-friendly prime the (word, reduction mode) kernel path of size 2^logn admits."""
+    L = lib()
+    ok = (lambda q: q < (1 << 60)) if red else (lambda q: bool(L.emu_lazy_full_ok(word_bytes, q, logn)))
+    return largest_friendly_prime(1 << logn, ok)

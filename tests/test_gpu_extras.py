@@ -270,3 +270,35 @@ def test_fused_kernels_for_other_ring_sizes(n, q, psi):
     assert (host(tntt.forward(plan, ta)) == co.cg_ntt(a, omega, q)).all()
     assert (host(tntt.inverse(plan, ta)) == co.cg_intt(a, omega, q)).all()
     assert torch.equal(tntt.inverse(plan, tntt.forward(plan, ta, twist=True), twist=True), ta)
+
+
+@pytest.mark.parametrize("wb,logn,red", [(4, 8, 0), (4, 12, 0), (4, 13, 0), (8, 8, 0), (8, 12, 0), (8, 12, 1), (8, 13, 1)])
+def test_largest_modulus_each_kernel_path_accepts(wb, logn, red):
+    # tightest lazy ranges: the largest NTT-friendly prime a path admits, rows of all q-1; every variant, the
+    # transform-domain kernels and the natural-order transforms against the oracle
+    import emu
+    import tntt
+
+    n = 1 << logn
+    q = emu.largest_modulus_of_path(wb, logn, red)
+    psi = tntt.find_psi(n, q)
+    plan = tntt.get_plan(n, q, psi, True)
+    assert plan.word_bytes == wb and plan.lazy_reduce == red, (q, plan.word_bytes, plan.lazy_reduce)
+    co = COracle()
+    npdt = np.uint32 if wb == 4 else np.uint64
+    sdt = np.int32 if wb == 4 else np.int64
+    rng = np.random.default_rng(logn)
+    rows = 21
+    a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    a[1] = q - 1
+    ta = torch.from_numpy(a.astype(npdt).view(sdt)).cuda()
+    tb = torch.from_numpy(b.astype(npdt).view(sdt)).cuda()
+    host = lambda t: t.cpu().numpy().view(npdt).astype(np.uint64)      # noqa: E731
+    want = co.nwc_poly_mult(a, b, psi, q, threads=8)
+    for v, desc in plan.variants():
+        assert (host(tntt.polymul(plan, ta, tb, variant=v)) == want).all(), (q, desc)
+    assert (host(tntt.polymul_spectrum(plan, ta, tntt.forward_spectrum(plan, tb))) == want).all(), q
+    assert (host(tntt.inverse(plan, ta)) == co.cg_intt(a, psi * psi % q, q)).all(), q
+    assert torch.equal(tntt.inverse(plan, tntt.forward(plan, ta, twist=True), twist=True), ta)

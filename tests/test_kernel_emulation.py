@@ -214,3 +214,41 @@ def test_emulated_kernels_at_other_sizes(wb, logn, logr, ppc, na, red, q, psi, c
     assert (emu.spectrum(wb, logn, logr, ppc, red, a, a, q, psi, 5).astype(np.uint64) == co.cg_ntt(a, omega, q)).all()
     assert (emu.spectrum(wb, logn, logr, ppc, red, a, a, q, psi, 7).astype(np.uint64) == co.cg_intt(a, omega, q)).all()
     assert emu.lib().emu_range_violations() == 0
+
+
+_largest_friendly_prime = emu.largest_friendly_prime
+
+
+#                 word logn logr ppc na red
+BOUNDARY_SHAPES = [(4, 8, 4, 16, 2, 0), (4, 10, 5, 8, 2, 0), (4, 12, 4, 1, 2, 0), (4, 13, 5, 1, 2, 0),
+                   (8, 8, 4, 16, 1, 0), (8, 12, 4, 1, 1, 0), (8, 13, 4, 1, 1, 0),
+                   (8, 8, 4, 16, 1, 1), (8, 12, 4, 1, 1, 1), (8, 12, 4, 1, 2, 1), (8, 13, 4, 1, 1, 1)]
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,na,red", BOUNDARY_SHAPES)
+def test_emulated_kernels_at_the_largest_modulus_each_path_accepts(wb, logn, logr, ppc, na, red, co):
+    # the lazy value ranges are tightest for the largest modulus a path admits: the largest NTT-friendly prime that
+    # still passes lazy_full_ok (reduction-free paths) or is below 2^60 (paths with per-pass reduction), with
+    # all-(q-1) rows; the emulation audits every butterfly for wrap-around
+    from tntt.rns import find_psi
+
+    L = emu.lib()
+    n = 1 << logn
+    ok = (lambda q: q < (1 << 60)) if red else (lambda q: bool(L.emu_lazy_full_ok(wb, q, logn)))
+    q = _largest_friendly_prime(n, ok)
+    assert ok(q) and (red or not ok(q + 2 * n * 64) or q > (1 << 59))
+    psi = find_psi(n, q)
+    rng = np.random.default_rng(logn + wb + red)
+    batch = ppc + 1
+    a = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    a[1] = q - 1
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    assert (emu.polymul(wb, logn, logr, ppc, na, red, a, b, q, psi).astype(np.uint64) == want).all(), q
+    assert emu.lib().emu_range_violations() == 0, q
+    if na == 1 or (wb, logn) in ((4, 8), (4, 10), (4, 12), (4, 13)):     # the plan's transform-domain shape
+        assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 1).astype(np.uint64) == want).all(), q
+        assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 0).astype(np.uint64) == a).all(), q
+        assert (emu.spectrum(wb, logn, logr, ppc, red, a, a, q, psi, 7).astype(np.uint64) == co.cg_intt(a, psi * psi % q, q)).all(), q
+        assert emu.lib().emu_range_violations() == 0, q
