@@ -185,8 +185,11 @@ void choose_small_batch_variants(tntt_plan *p) {
     for (size_t i = 0; i < vs.size(); ++i)
         // 64-bit words only: the 32-bit rows are short enough that the cluster barriers eat the gain (measured)
         if (vs[i].cluster > 0 && vs[i].word_bytes == 8 && tntt_variant_matches(p, (int)i)) {
+            cudaFuncAttributes attr{};
+            int clusters = 0;
+            if (vs[i].attributes(&attr, &clusters) != cudaSuccess || clusters <= 0) { cudaGetLastError(); continue; }
             I.cluster_variant = (int)i;
-            I.cluster_batch_max = sms / vs[i].cluster;
+            I.cluster_batch_max = sms / vs[i].cluster < clusters ? sms / vs[i].cluster : clusters;
             break;
         }
     static const char *small[] = {"u64_n12_r3_p1_a1_red1_b1_s0_t0"};

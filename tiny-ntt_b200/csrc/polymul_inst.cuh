@@ -54,10 +54,23 @@ template <class C, int CS, bool RED> struct PolymulClusterInst {
     static cudaError_t prepare() {
         return cudaFuncSetAttribute(polymul_cluster_kernel<C, CS, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     }
+    // for cluster variants `blocks_per_sm` reports how many CLUSTERS the device can hold at once (0: the device
+    // cannot co-schedule a cluster of this shape, e.g. under a partition with too few SMs per GPC)
     static cudaError_t attributes(cudaFuncAttributes *attr, int *blocks_per_sm) {
         cudaError_t e = cudaFuncGetAttributes(attr, polymul_cluster_kernel<C, CS, RED>);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, polymul_cluster_kernel<C, CS, RED>, C::P / CS, SMEM);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CS);
+        cfg.blockDim = dim3(C::P / CS);
+        cfg.dynamicSmemBytes = SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CS;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaOccupancyMaxActiveClusters(blocks_per_sm, polymul_cluster_kernel<C, CS, RED>, &cfg);
     }
 };
 #define TNTT_POLYMUL_CLUSTER(WT, WB, LN, LR, CS, RED)                                                                 \
