@@ -20,8 +20,12 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 12, 3, 1, 2, 0, 2),
     // small batches: one row per cluster of 4 CTAs, exchanges through distributed shared memory
     TNTT_POLYMUL_CLUSTER(uint32_t, 32, 12, 3, 4, 0),
+    // three CTAs per SM (80 registers): the four-CTA shapes above spill a little at 64 registers
+    TNTT_POLYMUL_VARIANT(uint32_t, 32, 8, 4, 16, 2, 0, 3),
+    TNTT_POLYMUL_VARIANT(uint32_t, 32, 12, 4, 1, 2, 0, 3),
     // sizes next to the reference's three (other NTT-friendly rings): N = 512, 2048, 8192
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 9, 5, 16, 2, 0, 2),
+    TNTT_POLYMUL_VARIANT(uint32_t, 32, 11, 4, 2, 2, 0, 3),
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 11, 4, 2, 2, 0, 4),
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 13, 5, 1, 2, 0, 2),
 };

@@ -38,9 +38,16 @@
 #endif
 
 using namespace tntt;
+#ifdef W_U32   // the 24-bit N = 4096 set of the reference (32-bit words, no intermediate reduction)
+using W = uint32_t;
+constexpr uint64_t Q = 8380417ull, PSI = 283817ull;
+constexpr bool kRed = false;
+#else
 using W = uint64_t;
-using C = Cfg<W, 12, W_LOGR, 1>;
 constexpr uint64_t Q = 1152921504606830593ull, PSI = 431606828070683274ull;
+constexpr bool kRed = true;
+#endif
+using C = Cfg<W, 12, W_LOGR, 1>;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -56,7 +63,7 @@ int main(int argc, char **argv) {
     const uint64_t psi_inv = host::modinv(PSI, Q), omega_inv = host::mulmod(psi_inv, psi_inv, Q), n_inv = host::modinv(n, Q);
     const Mod<W> mod = host::make_mod<W>(Q, 12);
     std::vector<Tw<W>> fwd = host::fwd_pyramid<W>(PSI, n, Q), inv = host::dit_pyramid<W>(omega_inv, n, Q);
-    const uint64_t r_mod_q = (uint64_t)((((host::u128)1) << 64) % Q);
+    const uint64_t r_mod_q = (uint64_t)((((host::u128)1) << (8 * sizeof(W))) % Q);
     PolymulTables<W> tb;
     tb.fwd_pyr = upload(fwd);
     tb.fwd_last = upload(host::fwd_last_table<W>(fwd, 12, W_LOGR));
@@ -67,13 +74,13 @@ int main(int argc, char **argv) {
     std::vector<W> a(rows * n), b(rows * n);
     uint64_t s = 88172645463325252ull;
     auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s % Q; };
-    for (size_t i = 0; i < rows * n; ++i) { a[i] = rnd(); b[i] = rnd(); }
-    for (uint32_t i = 0; i < n; ++i) { a[n + i] = Q - 1; b[n + i] = Q - 1; }   // row 1: worst case for the lazy ranges
+    for (size_t i = 0; i < rows * n; ++i) { a[i] = (W)rnd(); b[i] = (W)rnd(); }
+    for (uint32_t i = 0; i < n; ++i) { a[n + i] = (W)(Q - 1); b[n + i] = (W)(Q - 1); }   // row 1: worst case for the lazy ranges
     W *da = upload(a), *db = upload(b), *dc;
     CK(cudaMalloc(&dc, rows * n * sizeof(W)));
 
 #ifdef W_CLUSTER
-    auto kern = polymul_cluster_kernel<C, W_CLUSTER, true>;
+    auto kern = polymul_cluster_kernel<C, W_CLUSTER, kRed>;
     const size_t smem = 2 * (C::N / W_CLUSTER) * sizeof(W);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kern));
@@ -87,7 +94,7 @@ int main(int argc, char **argv) {
         CK(cudaLaunchKernelEx(&cfg, kern, (const W *)da, (const W *)db, dc, rows, tb, mod));
     };
 #else
-    auto kern = polymul_kernel<C, W_NA, true, W_MINB, W_STASH, W_TMA>;
+    auto kern = polymul_kernel<C, W_NA, kRed, W_MINB, W_STASH, W_TMA>;
     const size_t smem = (size_t)(W_NA + (W_STASH == 1 ? 1 : 0)) * C::N * sizeof(W) + (W_TMA ? kTwBufBytes + 16 : 0);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kern));
@@ -117,7 +124,7 @@ int main(int argc, char **argv) {
 #ifndef WHATIF_WRONG_RESULTS
     long bad = 0;
     for (int row = 0; row < 2; ++row) {
-        std::vector<W> want(n, 0);
+        std::vector<uint64_t> want(n, 0);
         for (uint32_t i = 0; i < n; ++i)
             for (uint32_t j = 0; j < n; ++j) {
                 const uint64_t p = host::mulmod(a[row * n + i], b[row * n + j], Q);
