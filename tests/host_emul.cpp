@@ -371,6 +371,7 @@ int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, co
     POLY_CASE(8, uint64_t, 9, 4, 8, 1, 1)
     POLY_CASE(8, uint64_t, 11, 4, 2, 1, 0)
     POLY_CASE(8, uint64_t, 11, 4, 2, 1, 1)
+    POLY_CASE(8, uint64_t, 11, 4, 2, 2, 1)
     POLY_CASE(8, uint64_t, 13, 4, 1, 1, 0)
     POLY_CASE(8, uint64_t, 13, 4, 1, 1, 1)
     return -1;

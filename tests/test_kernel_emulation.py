@@ -193,6 +193,7 @@ EXTRA_SIZES = [
     (4, 9, 5, 16, 2, 0, 8380417, 1718063), (4, 11, 4, 2, 2, 0, 8380417, 7901702), (4, 13, 5, 1, 2, 0, 67043329, 8157893),
     (8, 9, 4, 8, 1, 0, 8380417, 1718063), (8, 9, 4, 8, 1, 1, Q60, 984081769261068913),
     (8, 11, 4, 2, 1, 0, 8380417, 7901702), (8, 11, 4, 2, 1, 1, Q60, 644283108363935541),
+    (8, 11, 4, 2, 2, 1, Q60, 644283108363935541),
     (8, 13, 4, 1, 1, 0, 67043329, 8157893), (8, 13, 4, 1, 1, 1, Q60, 527760526715669589),
 ]
 

@@ -11,6 +11,7 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 9, 4, 8, 1, 0, 2),
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 9, 4, 8, 1, 1, 2),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 11, 4, 2, 1, 0, 3, 1),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 11, 4, 2, 2, 1, 2),          // first match = default (25.2 vs 24.1 M/s measured)
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 11, 4, 2, 1, 1, 3, 1),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 13, 4, 1, 1, 0, 1, 1),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 13, 4, 1, 1, 1, 1, 1),
