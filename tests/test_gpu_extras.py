@@ -302,3 +302,32 @@ def test_largest_modulus_each_kernel_path_accepts(wb, logn, red):
     assert (host(tntt.polymul_spectrum(plan, ta, tntt.forward_spectrum(plan, tb))) == want).all(), q
     assert (host(tntt.inverse(plan, ta)) == co.cg_intt(a, psi * psi % q, q)).all(), q
     assert torch.equal(tntt.inverse(plan, tntt.forward(plan, ta, twist=True), twist=True), ta)
+
+
+@pytest.mark.parametrize("wb,logn,red", [(4, 14, 0), (4, 15, 0), (8, 14, 0), (8, 14, 1), (8, 15, 0), (8, 15, 1)])
+def test_rows_longer_than_one_cta_run_on_clusters(wb, logn, red):
+    # N = 16384 / 32768: a row does not fit one CTA's shared memory; the fused product runs one row per
+    # thread-block cluster (4 / 8 CTAs, every exchange through distributed shared memory).  Largest admissible
+    # modulus of each path, rows of all q-1, ragged batch sizes.
+    import emu
+    import tntt
+
+    n = 1 << logn
+    q = emu.largest_modulus_of_path(wb, logn, red)
+    psi = tntt.find_psi(n, q)
+    plan = tntt.get_plan(n, q, psi, True)
+    assert plan.word_bytes == wb and plan.lazy_reduce == red and plan.fused == 1
+    names = dict((v, d.split()[0]) for v, d in plan.variants())
+    assert names[plan.default_variant].endswith("_c4" if logn == 14 else "_c8")
+    co = COracle()
+    npdt = np.uint32 if wb == 4 else np.uint64
+    sdt = np.int32 if wb == 4 else np.int64
+    rng = np.random.default_rng(logn)
+    for rows in (1, 7, 40):
+        a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+        b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+        a[0], b[0] = q - 1, q - 1
+        ta = torch.from_numpy(a.astype(npdt).view(sdt)).cuda()
+        tb = torch.from_numpy(b.astype(npdt).view(sdt)).cuda()
+        got = tntt.polymul(plan, ta, tb).cpu().numpy().view(npdt).astype(np.uint64)
+        assert (got == co.nwc_poly_mult(a, b, psi, q, threads=8)).all(), (q, rows)

@@ -163,6 +163,14 @@ int choose_default_variant(const tntt_plan *p) {
             if (!strcmp(vs[i].name, name) && tntt_variant_matches(p, (int)i)) return (int)i;
     for (size_t i = 0; i < vs.size(); ++i)
         if (!vs[i].cluster && tntt_variant_matches(p, (int)i)) return (int)i;
+    // rows too long for one CTA (N = 16384, 32768): the cluster kernel is the only fused shape
+    for (size_t i = 0; i < vs.size(); ++i)
+        if (vs[i].cluster && tntt_variant_matches(p, (int)i)) {
+            cudaFuncAttributes attr{};
+            int clusters = 0;
+            if (vs[i].attributes(&attr, &clusters) == cudaSuccess && clusters > 0) return (int)i;
+            cudaGetLastError();
+        }
     return -1;
 }
 

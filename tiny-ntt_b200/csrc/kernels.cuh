@@ -236,13 +236,13 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
     }
     if constexpr (B > LO) fwd_stage<C, PASS, NA, RED, B - 1, SMEM_TW, PRE, ALLPRE>(x, tid, tb, mod, stab, pre_t);
 }
-// all twiddles of forward pass PASS (a pass that runs all log2 R stages), slot = 2^(LOGR-1-kb) - 1 + g
+// all twiddles of forward pass PASS (its stages pair over register bits kb = bhi-LO-1 .. 0; a pass that does not
+// run all log2 R stages leaves the low slots unused), slot = 2^(LOGR-1-kb) - 1 + g
 template <class C, int PASS> TNTT_HD void fwd_load_pass_twiddles(Tw<typename C::W> (&t)[C::R - 1], int tid,
                                                                  const PolymulTables<typename C::W> &tb) {
     constexpr int LO = C::fwd_lo(PASS);
-    static_assert(C::fwd_bhi(PASS) - LO == C::LOGR, "full passes only");
 #pragma unroll
-    for (int kb = C::LOGR - 1; kb >= 0; --kb) {
+    for (int kb = C::fwd_bhi(PASS) - LO - 1; kb >= 0; --kb) {
         const int s = C::LOGN - 1 - (LO + kb);
 #pragma unroll
         for (int g = 0; g < (C::R >> (kb + 1)); ++g) {
@@ -347,13 +347,12 @@ TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typenam
                       const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
     dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS), SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
 }
-// all twiddles of inverse pass PASS (full passes only), slot = 2^kb - 1 + j; slot 0 of pass 0 is the trivial twiddle 1
+// all twiddles of inverse pass PASS (stages B = blo .. bhi-1, kb = B - LO), slot = 2^kb - 1 + j; slot 0 of pass 0 is the trivial twiddle 1
 template <class C, int PASS> TNTT_HD void dit_load_pass_twiddles(Tw<typename C::W> (&t)[C::R - 1], int tid,
                                                                  const DitTables<typename C::W> &dt) {
     constexpr int LO = C::inv_lo(PASS);
-    static_assert(C::inv_bhi(PASS) - C::inv_blo(PASS) == C::LOGR && LO == C::inv_blo(PASS), "full passes only");
 #pragma unroll
-    for (int kb = 0; kb < C::LOGR; ++kb) {
+    for (int kb = C::inv_blo(PASS) - LO; kb < C::inv_bhi(PASS) - LO; ++kb) {
         const int B = LO + kb;
 #pragma unroll
         for (int j = 0; j < (1 << kb); ++j) {
@@ -838,7 +837,7 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
                        size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
                        const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
-    static_assert(C::PPC == 1 && C::LOGN % C::LOGR == 0 && C::P % CS == 0, "cluster kernel: full passes, one row per cluster");
+    static_assert(C::PPC == 1 && C::P % CS == 0, "cluster kernel: one row per cluster");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W *tiles = reinterpret_cast<W *>(smem_raw);                 // two buffers of N / CS words
     const int gtid = (int)cluster_ctarank() * (C::P / CS) + (int)threadIdx.x;

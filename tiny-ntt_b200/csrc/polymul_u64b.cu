@@ -15,6 +15,12 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 11, 4, 2, 1, 1, 3, 1),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 13, 4, 1, 1, 0, 1, 1),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 13, 4, 1, 1, 1, 1, 1),
+    // rows that do not fit one CTA: one row per thread-block cluster (4 / 8 CTAs of 256 threads x 16 coefficients),
+    // every exchange through distributed shared memory
+    TNTT_POLYMUL_CLUSTER(uint64_t, 64, 14, 4, 4, 0),
+    TNTT_POLYMUL_CLUSTER(uint64_t, 64, 14, 4, 4, 1),
+    TNTT_POLYMUL_CLUSTER(uint64_t, 64, 15, 4, 8, 0),
+    TNTT_POLYMUL_CLUSTER(uint64_t, 64, 15, 4, 8, 1),
 };
 const PolymulVariant *polymul_variants_u64b(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));

@@ -14,6 +14,32 @@ import tntt  # noqa: E402
 Q60 = (1 << 60) - (1 << 14) + 1
 RINGS = [(512, 8380417, 1718063), (2048, 8380417, 7901702), (8192, 67043329, 8157893),
          (512, Q60, 984081769261068913), (2048, Q60, 644283108363935541), (8192, Q60, 527760526715669589)]
+# rows longer than one CTA: fused product on thread-block clusters only (no transform-domain kernels)
+BIG = [(16384, 73695233, 35902597), (32768, 69206017, 3229917),
+       (16384, 1152921504606748673, 641000223749548346), (32768, 1152921504606584833, 1100972123716672435)]
+for n, q, psi in BIG:
+    plan = tntt.get_plan(n, q, psi, True)
+    rows = (256 << 20) // (n * plan.word_bytes)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randint(0, q, (rows, n), generator=g, device="cuda", dtype=torch.int64).to(plan.dtype)
+    b = torch.randint(0, q, (rows, n), generator=g, device="cuda", dtype=torch.int64).to(plan.dtype)
+    c = torch.empty_like(a)
+    for _ in range(3):
+        tntt.polymul(plan, a, b, out=c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        tntt.polymul(plan, a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    per_s = rows / (e0.elapsed_time(e1) / 10 * 1e-3)
+    print(json.dumps({"n": n, "q_bits": q.bit_length(), "word": plan.word_bytes, "rows": rows, "polymul_per_s": per_s,
+                      "polymul_GBps": per_s * 3 * n * plan.word_bytes / 1e9,
+                      "kernel": dict(plan.variants())[plan.default_variant].split()[0]}), flush=True)
+    del a, b, c
+    torch.cuda.empty_cache()
+
 for n, q, psi in RINGS:
     plan = tntt.get_plan(n, q, psi, True)
     rows = (512 << 20) // (n * plan.word_bytes)          # 512 MiB per operand: well beyond L2
