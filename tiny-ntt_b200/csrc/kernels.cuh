@@ -831,8 +831,8 @@ __device__ __forceinline__ void cluster_inverse_rest(typename C::W (&x)[C::R], t
 }
 
 // launched with a cluster dimension of CS (cudaLaunchKernelEx); grid = rows * CS CTAs of P / CS threads
-template <class C, int CS, bool RED>
-__global__ void __launch_bounds__(C::P / CS, 1)
+template <class C, int CS, bool RED, int MINB = 1>
+__global__ void __launch_bounds__(C::P / CS, MINB)
 polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
                        size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
                        const __grid_constant__ Mod<typename C::W> mod) {

@@ -29,7 +29,7 @@ template <class C, int NA, bool RED, int MINB, int STASH = 0, int TMA = 0> struc
 };
 
 // one row per cluster of CS CTAs (small batches); launched with a cluster-dimension attribute
-template <class C, int CS, bool RED> struct PolymulClusterInst {
+template <class C, int CS, bool RED, int MINB = 1> struct PolymulClusterInst {
     using W = typename C::W;
     static constexpr size_t SMEM = 2 * (size_t)(C::N / CS) * sizeof(W);
     static cudaError_t launch(const void *a, const void *b, void *c, size_t batch, const void *tables, const void *mod,
@@ -47,17 +47,17 @@ template <class C, int CS, bool RED> struct PolymulClusterInst {
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, polymul_cluster_kernel<C, CS, RED>, static_cast<const W *>(a), static_cast<const W *>(b),
+        return cudaLaunchKernelEx(&cfg, polymul_cluster_kernel<C, CS, RED, MINB>, static_cast<const W *>(a), static_cast<const W *>(b),
                                   static_cast<W *>(c), batch, *static_cast<const PolymulTables<W> *>(tables),
                                   *static_cast<const Mod<W> *>(mod));
     }
     static cudaError_t prepare() {
-        return cudaFuncSetAttribute(polymul_cluster_kernel<C, CS, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        return cudaFuncSetAttribute(polymul_cluster_kernel<C, CS, RED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     }
     // for cluster variants `blocks_per_sm` reports how many CLUSTERS the device can hold at once (0: the device
     // cannot co-schedule a cluster of this shape, e.g. under a partition with too few SMs per GPC)
     static cudaError_t attributes(cudaFuncAttributes *attr, int *blocks_per_sm) {
-        cudaError_t e = cudaFuncGetAttributes(attr, polymul_cluster_kernel<C, CS, RED>);
+        cudaError_t e = cudaFuncGetAttributes(attr, polymul_cluster_kernel<C, CS, RED, MINB>);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(CS);
@@ -70,16 +70,17 @@ template <class C, int CS, bool RED> struct PolymulClusterInst {
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        return cudaOccupancyMaxActiveClusters(blocks_per_sm, polymul_cluster_kernel<C, CS, RED>, &cfg);
+        return cudaOccupancyMaxActiveClusters(blocks_per_sm, polymul_cluster_kernel<C, CS, RED, MINB>, &cfg);
     }
 };
-#define TNTT_POLYMUL_CLUSTER(WT, WB, LN, LR, CS, RED)                                                                 \
+#define TNTT_POLYMUL_CLUSTER(WT, WB, LN, LR, CS, RED) TNTT_POLYMUL_CLUSTER_B(WT, WB, LN, LR, CS, RED, 1)
+#define TNTT_POLYMUL_CLUSTER_B(WT, WB, LN, LR, CS, RED, MINB)                                                         \
     PolymulVariant {                                                                                                  \
-        "u" #WB "_n" #LN "_r" #LR "_p1_a1_red" #RED "_c" #CS, WB / 8, LN, LR, 1, 1, RED, Cfg<WT, LN, LR, 1>::P / CS, 1, \
-            PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::SMEM,                                              \
-            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::launch,                                           \
-            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::prepare,                                          \
-            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0)>::attributes, CS                                    \
+        "u" #WB "_n" #LN "_r" #LR "_p1_a1_red" #RED "_b" #MINB "_c" #CS, WB / 8, LN, LR, 1, 1, RED,                    \
+            Cfg<WT, LN, LR, 1>::P / CS, MINB, PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::SMEM,       \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::launch,                                     \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::prepare,                                    \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::attributes, CS                              \
     }
 
 #define TNTT_POLYMUL_VARIANT(WT, WB, LN, LR, PPC, NA, RED, MINB) TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, 0, 0)

@@ -29,7 +29,9 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 11, 4, 2, 2, 0, 4),
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 13, 5, 1, 2, 0, 2),
     // rows that do not fit one CTA: one row per thread-block cluster
+    TNTT_POLYMUL_CLUSTER_B(uint32_t, 32, 14, 4, 4, 0, 2),
     TNTT_POLYMUL_CLUSTER(uint32_t, 32, 14, 4, 4, 0),
+    TNTT_POLYMUL_CLUSTER_B(uint32_t, 32, 15, 4, 8, 0, 2),
     TNTT_POLYMUL_CLUSTER(uint32_t, 32, 15, 4, 8, 0),
 };
 const PolymulVariant *polymul_variants_u32(int *count) {
