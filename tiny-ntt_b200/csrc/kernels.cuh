@@ -807,26 +807,28 @@ __device__ __forceinline__ void cluster_exchange(typename C::W (&x)[C::R], typen
     for (int k = 0; k < C::R; ++k) x[k] = buf[k * T + (gtid % T)];
 }
 
-template <class C, int CS, bool RED, int XI, int PASS = 1>
+// PRELOAD: fetch the next pass's twiddles into registers before the cluster barrier, so that their L2 latency
+// overlaps the exchange
+template <class C, int CS, bool RED, bool PRELOAD, int XI, int PASS = 1>
 __device__ __forceinline__ void cluster_forward_rest(typename C::W (&x)[1][C::R], typename C::W *tiles, int gtid,
                                                      const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod) {
     if constexpr (PASS < C::NPASS) {
-        Tw<typename C::W> tw[C::R - 1];
-        fwd_load_pass_twiddles<C, PASS>(tw, gtid, tb);
+        Tw<typename C::W> tw[PRELOAD ? C::R - 1 : 1];
+        if constexpr (PRELOAD) fwd_load_pass_twiddles<C, PASS>(tw, gtid, tb);
         cluster_exchange<C, CS, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[0], tiles + ((XI + PASS) & 1) * (C::N / CS), gtid);
-        fwd_pass<C, PASS, 1, RED, false, false, true>(x, gtid, tb, mod, nullptr, tw);
-        cluster_forward_rest<C, CS, RED, XI, PASS + 1>(x, tiles, gtid, tb, mod);
+        fwd_pass<C, PASS, 1, RED, false, false, PRELOAD>(x, gtid, tb, mod, nullptr, tw);
+        cluster_forward_rest<C, CS, RED, PRELOAD, XI, PASS + 1>(x, tiles, gtid, tb, mod);
     }
 }
-template <class C, int CS, bool RED, int IN_BND, int XI, int PASS = 1>
+template <class C, int CS, bool RED, bool PRELOAD, int IN_BND, int XI, int PASS = 1>
 __device__ __forceinline__ void cluster_inverse_rest(typename C::W (&x)[C::R], typename C::W *tiles, int gtid,
                                                      const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
     if constexpr (PASS < C::NPASS) {
-        Tw<typename C::W> tw[C::R - 1];
-        dit_load_pass_twiddles<C, PASS>(tw, gtid, dt);
+        Tw<typename C::W> tw[PRELOAD ? C::R - 1 : 1];
+        if constexpr (PRELOAD) dit_load_pass_twiddles<C, PASS>(tw, gtid, dt);
         cluster_exchange<C, CS, C::inv_lo(PASS - 1), C::inv_lo(PASS)>(x, tiles + ((XI + PASS) & 1) * (C::N / CS), gtid);
-        dit_pass<C, PASS, RED, IN_BND, false, false, true>(x, gtid, dt, mod, nullptr, tw);
-        cluster_inverse_rest<C, CS, RED, IN_BND, XI, PASS + 1>(x, tiles, gtid, dt, mod);
+        dit_pass<C, PASS, RED, IN_BND, false, false, PRELOAD>(x, gtid, dt, mod, nullptr, tw);
+        cluster_inverse_rest<C, CS, RED, PRELOAD, IN_BND, XI, PASS + 1>(x, tiles, gtid, dt, mod);
     }
 }
 
@@ -845,6 +847,7 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
     const bool active = row < batch;
     const size_t off = active ? row * C::N : 0;
     constexpr int NX = C::NPASS - 1;                            // exchanges per transform
+    constexpr bool PRELOAD = true;   // measured: also (slightly) better with two CTAs per SM (3.53 vs 3.32 M/s, 27-bit N = 16384)
 #if defined(TNTT_X_EMPTY_KERNEL)
     if (batch) return;   // what-if only: launch overhead calibration
 #endif
@@ -854,11 +857,11 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
     row_load<C>(x[0], a + off, gtid, active);
     row_load<C>(fa, b + off, gtid, active);                      // b's latency overlaps a's transform
     fwd_pass<C, 0, 1, RED>(x, gtid, tb, mod);
-    cluster_forward_rest<C, CS, RED, 0>(x, tiles, gtid, tb, mod);
+    cluster_forward_rest<C, CS, RED, PRELOAD, 0>(x, tiles, gtid, tb, mod);
 #pragma unroll
     for (int k = 0; k < C::R; ++k) { const W t = x[0][k]; x[0][k] = fa[k]; fa[k] = t; }
     fwd_pass<C, 0, 1, RED>(x, gtid, tb, mod);
-    cluster_forward_rest<C, CS, RED, NX>(x, tiles, gtid, tb, mod);
+    cluster_forward_rest<C, CS, RED, PRELOAD, NX>(x, tiles, gtid, tb, mod);
 #pragma unroll
     for (int k = 0; k < C::R; ++k) {
         W u = fa[k];
@@ -866,7 +869,7 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
         fa[k] = mont_mul(u, x[0][k], mod);
     }
     dit_pass<C, 0, RED, pointwise_out_bound<C, RED>()>(fa, gtid, tb.inv, mod);
-    cluster_inverse_rest<C, CS, RED, pointwise_out_bound<C, RED>(), 2 * NX>(fa, tiles, gtid, tb.inv, mod);
+    cluster_inverse_rest<C, CS, RED, PRELOAD, pointwise_out_bound<C, RED>(), 2 * NX>(fa, tiles, gtid, tb.inv, mod);
     row_store_scaled<C, 1>(fa, c + off, gtid, active, tb.post, Tw<W>{0, 0}, mod);
     // no trailing barrier: the last remote store into this CTA's shared memory precedes the last exchange's barrier
 }
