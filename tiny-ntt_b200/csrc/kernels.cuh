@@ -709,7 +709,6 @@ spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__r
     const bool active = poly < batch;
     const size_t off = active ? poly * C::N : 0;
     W x[C::R];
-    if constexpr (TABLE) prefetch_post<C>(tid, post);   // the store table is needed last: start pulling it towards L1 now
     if constexpr (!NATURAL) {
         row_load<C>(x, in + off, tid, active);                  // spectrum order == the coalesced row pattern
     } else if constexpr (C::P <= 32) {
