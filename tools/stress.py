@@ -1,0 +1,88 @@
+#!/usr/bin/env python3
+"""Randomised parity stress: random NTT-friendly primes (24..60 bits), every fused size, random batch sizes,
+every variant and the transform-domain / natural-order routes against the C oracle.  usage: stress.py [SECONDS]"""
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tiny-ntt_b200"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import tntt  # noqa: E402
+from oracle.cpu_ref import COracle  # noqa: E402
+
+
+def is_prime(n):
+    if n < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % p == 0:
+            return n == p
+    d, r = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        r += 1
+    for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(r - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    rnd = random.Random(2026)
+    co = COracle()
+    t0, cases = time.time(), 0
+    while time.time() - t0 < budget:
+        logn = rnd.choice([8, 9, 10, 11, 12, 13, 14, 15])
+        n = 1 << logn
+        bits = rnd.choice([20, 23, 26, 28, 31, 40, 50, 58, 59, 60])
+        if bits <= logn + 2:
+            continue
+        while True:
+            k = rnd.randrange(1 << (bits - logn - 2), 1 << (bits - logn - 1))
+            q = k * 2 * n + 1
+            if q.bit_length() == bits and is_prime(q):
+                break
+        psi = tntt.find_psi(n, q)
+        tntt.clear_plan_cache()
+        plan = tntt.get_plan(n, q, psi, True)
+        npdt, sdt = (np.uint32, np.int32) if plan.word_bytes == 4 else (np.uint64, np.int64)
+        rows = rnd.choice([1, 2, 3, 17, 37, 38, 149, 200]) if logn <= 13 else rnd.choice([1, 3, 9])
+        rng = np.random.default_rng(cases)
+        a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+        b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+        a[0] = q - 1
+        if rows > 1:
+            b[1] = q - 1
+        ta = torch.from_numpy(a.astype(npdt).view(sdt)).cuda()
+        tb = torch.from_numpy(b.astype(npdt).view(sdt)).cuda()
+        host = lambda t: t.cpu().numpy().view(npdt).astype(np.uint64)      # noqa: E731
+        want = co.nwc_poly_mult(a, b, psi, q, threads=8)
+        assert (host(tntt.polymul(plan, ta, tb)) == want).all(), ("dispatch", n, q, rows)
+        for v, d in plan.variants():
+            assert (host(tntt.polymul(plan, ta, tb, variant=v)) == want).all(), (d, n, q, rows)
+        if plan.spectrum:
+            sb = tntt.forward_spectrum(plan, tb)
+            assert (host(tntt.polymul_spectrum(plan, ta, sb)) == want).all(), ("spectrum", n, q, rows)
+            assert (host(tntt.inverse_spectrum(plan, tntt.pointwise(plan, tntt.forward_spectrum(plan, ta), sb))) == want).all()
+        omega = psi * psi % q
+        assert (host(tntt.forward(plan, ta)) == co.cg_ntt(a, omega, q)).all(), ("cg_ntt", n, q, rows)
+        assert (host(tntt.inverse(plan, ta)) == co.cg_intt(a, omega, q)).all(), ("cg_intt", n, q, rows)
+        cases += 1
+    print(f"stress ok: {cases} random (n, q, batch) cases in {time.time() - t0:.0f} s")
+
+
+if __name__ == "__main__":
+    main()
