@@ -144,7 +144,7 @@ int tntt_butterfly_batch(int device, uint64_t q, const uint64_t *a, const uint64
  *   tntt_spectrum_inverse : spectrum -> coefficients, i.e. untwist(cg_intt(.)) (cg_ntt.py:90-92)
  *   tntt_polymul_spectrum : c = a * b in Z_q[x]/(x^n+1) with b given as spectrum; b_rows = batch (one per row) or
  *                           1 (one spectrum shared by the whole batch).  Bit-identical to tntt_polymul.
- * Available when tntt_plan_info.spectrum is 1 (plans created from psi with n in {256, 512, 1024, 2048, 4096, 8192}). */
+ * Available when tntt_plan_info.spectrum is 1 (plans created from psi with n in {256, 512, ..., 32768}). */
 int tntt_spectrum_forward(const tntt_plan *plan, const void *in, void *out, size_t batch, void *cuda_stream);
 int tntt_spectrum_inverse(const tntt_plan *plan, const void *in, void *out, size_t batch, void *cuda_stream);
 int tntt_polymul_spectrum(const tntt_plan *plan, const void *a, const void *b_spectrum, void *c, size_t batch,

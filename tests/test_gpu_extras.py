@@ -330,4 +330,20 @@ def test_rows_longer_than_one_cta_run_on_clusters(wb, logn, red):
         ta = torch.from_numpy(a.astype(npdt).view(sdt)).cuda()
         tb = torch.from_numpy(b.astype(npdt).view(sdt)).cuda()
         got = tntt.polymul(plan, ta, tb).cpu().numpy().view(npdt).astype(np.uint64)
-        assert (got == co.nwc_poly_mult(a, b, psi, q, threads=8)).all(), (q, rows)
+        want = co.nwc_poly_mult(a, b, psi, q, threads=8)
+        assert (got == want).all(), (q, rows)
+        # transform-domain kernels on clusters
+        host = lambda t: t.cpu().numpy().view(npdt).astype(np.uint64)      # noqa: E731
+        assert plan.spectrum == 1
+        sa, sb = tntt.forward_spectrum(plan, ta), tntt.forward_spectrum(plan, tb)
+        assert host(sa).max() < q
+        assert torch.equal(tntt.inverse_spectrum(plan, sa), ta), (q, rows)
+        assert (host(tntt.polymul_spectrum(plan, ta, sb)) == want).all(), (q, rows)
+        assert (host(tntt.inverse_spectrum(plan, tntt.pointwise(plan, sa, sb))) == want).all(), (q, rows)
+        if rows > 1:
+            shared = co.nwc_poly_mult(a, np.broadcast_to(b[1], a.shape).copy(), psi, q, threads=8)
+            assert (host(tntt.polymul_spectrum(plan, ta, sb[1])) == shared).all(), (q, rows)
+    # natural-order transforms of these sizes run the literal schedule
+    omega = psi * psi % q
+    assert (host(tntt.forward(plan, ta[:2])) == co.cg_ntt(a[:2], omega, q)).all()
+    assert sorted(host(sa)[0].tolist()) == sorted(host(tntt.forward(plan, ta[:1], twist=True))[0].tolist())

@@ -373,7 +373,7 @@ int transform(const tntt_plan *p, const void *in, void *out, size_t batch, bool 
     if (batch == 0) return TNTT_OK;
     DeviceSetter ds(p->info.device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->spectrum && !(flags & TNTT_REDUCE_INPUT) && (!(flags & TNTT_TWIST) || p->info.spectrum))
+    if (p->spectrum && p->spectrum->forward_natural && !(flags & TNTT_REDUCE_INPUT) && (!(flags & TNTT_TWIST) || p->info.spectrum))
         return p->info.word_bytes == 4 ? natural_transform<uint32_t>(p, in, out, batch, inverse, flags, st)
                                        : natural_transform<uint64_t>(p, in, out, batch, inverse, flags, st);
     if (p->xform) return p->info.word_bytes == 4 ? fast_transform<uint32_t>(p, in, out, batch, inverse, flags, st)
@@ -417,7 +417,7 @@ template <typename W> int spectrum_op(const tntt_plan *p, int op, const void *a,
 int spectrum_entry(const tntt_plan *p, int op, const void *a, const void *b, void *out, size_t batch, size_t b_rows, void *stream) {
     int rc = check_io(p, a, op == 2 ? b : a, batch);
     if (rc) return rc;
-    if (!p->info.spectrum) return fail(TNTT_UNSUPPORTED_N, "no transform-domain kernels for this plan (needs psi and a fused size: n in {256, 512, 1024, 2048, 4096, 8192})");
+    if (!p->info.spectrum) return fail(TNTT_UNSUPPORTED_N, "no transform-domain kernels for this plan (needs psi and a fused size: n in {256, 512, ..., 32768})");
     if (batch == 0) return TNTT_OK;
     if (!out || ((uintptr_t)out & 15)) return fail(TNTT_BAD_ARG, "output must be a 16-byte aligned device pointer");
     if (op == 2 && b_rows != 1 && b_rows != batch) return fail(TNTT_BAD_ARG, "b_rows must be 1 (shared spectrum) or the batch size");

@@ -874,6 +874,62 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
     // no trailing barrier: the last remote store into this CTA's shared memory precedes the last exchange's barrier
 }
 
+// Transform-domain kernels for rows that live on a cluster (N = 16384, 32768): the halves of polymul_cluster_kernel.
+//   MODE 1: spectrum_forward   (in = a, out = c)
+//   MODE 2: spectrum_inverse   (in = a spectrum, out = c; post = psi^-i N^-1 table)
+//   MODE 3: polymul_spectrum   (a coefficients, b spectrum with row stride b_stride, out = c; post = tb.post)
+// The spectrum order is the same as in the one-CTA kernels: word k*P + t = bit-reversed-order element t*R + k, with t
+// the row-wide thread index (cluster rank * threads + threadIdx).
+template <class C, int CS, bool RED, int MINB, int MODE>
+__global__ void __launch_bounds__(C::P / CS, MINB)
+spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
+                        size_t batch, size_t b_stride, const __grid_constant__ PolymulTables<typename C::W> tb,
+                        const Tw<typename C::W> *__restrict__ post, const __grid_constant__ Mod<typename C::W> mod) {
+    using W = typename C::W;
+    static_assert(C::PPC == 1 && C::P % CS == 0 && MODE >= 1 && MODE <= 3, "cluster kernel: one row per cluster");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tiles = reinterpret_cast<W *>(smem_raw);
+    const int gtid = (int)cluster_ctarank() * (C::P / CS) + (int)threadIdx.x;
+    const size_t row = blockIdx.x / CS;
+    const bool active = row < batch;
+    const size_t off = active ? row * C::N : 0;
+    constexpr int NX = C::NPASS - 1;
+    W fa[C::R];
+    if constexpr (MODE == 2) {
+        row_load<C>(fa, a + off, gtid, active);
+        dit_pass<C, 0, RED, 1>(fa, gtid, tb.inv, mod);
+        cluster_inverse_rest<C, CS, RED, true, 1, 0>(fa, tiles, gtid, tb.inv, mod);
+        row_store_scaled<C, 1>(fa, c + off, gtid, active, post, Tw<W>{0, 0}, mod);
+    } else {
+        W x[1][C::R];
+        const W *brow = b + (active ? row * b_stride : 0);
+        if constexpr (MODE == 3) {
+            for (int line = gtid; b_stride != 0 && line < (int)(C::N * sizeof(W) / 128); line += C::P)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(brow) + (size_t)line * 128));
+        }
+        row_load<C>(x[0], a + off, gtid, active);
+        fwd_pass<C, 0, 1, RED>(x, gtid, tb, mod);
+        cluster_forward_rest<C, CS, RED, true, 0>(x, tiles, gtid, tb, mod);
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < C::R; ++k) {
+                const W v = csub(shoup_mul(x[0][k], (W)1, mod.one_p, mod.nq), mod.q);
+                if (active) st_stream(c + off + (k << C::LOGP) + gtid, v);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < C::R; ++k) {
+                W u = x[0][k];
+                if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
+                fa[k] = mont_mul(u, __ldg(brow + (k << C::LOGP) + gtid), mod);
+            }
+            dit_pass<C, 0, RED, 2>(fa, gtid, tb.inv, mod);
+            cluster_inverse_rest<C, CS, RED, true, 2, NX>(fa, tiles, gtid, tb.inv, mod);
+            row_store_scaled<C, 1>(fa, c + off, gtid, active, post, Tw<W>{0, 0}, mod);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // standalone natural-order transform (cg_ntt / cg_intt semantics, new_reference/cg_ntt.py:29-75):
 //   out = post * DFT_root(pre * in), all in natural order.  The bit-reversal of cg_ntt.py:39 /

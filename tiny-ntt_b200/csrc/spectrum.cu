@@ -58,6 +58,57 @@ template <class C, bool RED, int MINB> struct SpectrumInst {
     }
 };
 
+// rows on a thread-block cluster (N = 16384, 32768): spectrum order only, no natural-order kernels
+template <class C, int CS, bool RED, int MINB> struct SpectrumClusterInst {
+    using W = typename C::W;
+    static constexpr size_t SMEM = 2 * (size_t)(C::N / CS) * sizeof(W);
+    template <int MODE>
+    static cudaError_t launch(const void *a, const void *b, void *c, size_t batch, size_t b_stride, const void *tables,
+                              const void *post, const void *mod, cudaStream_t st) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(batch * CS));
+        cfg.blockDim = dim3(C::P / CS);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CS;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, spectrum_cluster_kernel<C, CS, RED, MINB, MODE>, static_cast<const W *>(a),
+                                  static_cast<const W *>(b), static_cast<W *>(c), batch, b_stride,
+                                  *static_cast<const PolymulTables<W> *>(tables), static_cast<const Tw<W> *>(post),
+                                  *static_cast<const Mod<W> *>(mod));
+    }
+    static cudaError_t forward(const void *in, void *out, size_t batch, const void *tables, const void *mod, cudaStream_t st) {
+        return launch<1>(in, nullptr, out, batch, 0, tables, nullptr, mod, st);
+    }
+    static cudaError_t inverse(const void *in, void *out, size_t batch, const void *tables, const void *post, const void *mod,
+                               cudaStream_t st) {
+        return launch<2>(in, nullptr, out, batch, 0, tables, post, mod, st);
+    }
+    static cudaError_t polymul(const void *a, const void *bspec, void *c, size_t batch, size_t b_stride, const void *tables,
+                               const void *mod, cudaStream_t st) {
+        return launch<3>(a, bspec, c, batch, b_stride, tables, static_cast<const PolymulTables<W> *>(tables)->post, mod, st);
+    }
+    static cudaError_t prepare() {
+        cudaError_t e = cudaFuncSetAttribute(spectrum_cluster_kernel<C, CS, RED, MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_cluster_kernel<C, CS, RED, MINB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_cluster_kernel<C, CS, RED, MINB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        return e;
+    }
+};
+#define TNTT_SPECTRUM_CLUSTER(WT, WB, LN, LR, CS, RED, MINB)                                                 \
+    SpectrumVariant {                                                                                        \
+        "sp_u" #WB "_n" #LN "_r" #LR "_red" #RED "_c" #CS, WB / 8, LN, LR, 1, RED,                              \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::forward,                           \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::inverse,                           \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::polymul,                           \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::prepare, nullptr, nullptr          \
+    }
+
 #define TNTT_SPECTRUM_VARIANT(WT, WB, LN, LR, PPC, RED, MINB)                                                \
     SpectrumVariant {                                                                                        \
         "sp_u" #WB "_n" #LN "_r" #LR "_p" #PPC "_red" #RED, WB / 8, LN, LR, PPC, RED,                          \
@@ -90,6 +141,13 @@ static const SpectrumVariant kVariants[] = {
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 11, 4, 2, 1, 3),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 13, 4, 1, 0, 1),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 13, 4, 1, 1, 1),
+    // N = 16384, 32768: on clusters
+    TNTT_SPECTRUM_CLUSTER(uint32_t, 32, 14, 4, 4, 0, 2),
+    TNTT_SPECTRUM_CLUSTER(uint32_t, 32, 15, 4, 8, 0, 2),
+    TNTT_SPECTRUM_CLUSTER(uint64_t, 64, 14, 4, 4, 0, 2),
+    TNTT_SPECTRUM_CLUSTER(uint64_t, 64, 14, 4, 4, 1, 2),
+    TNTT_SPECTRUM_CLUSTER(uint64_t, 64, 15, 4, 8, 0, 2),
+    TNTT_SPECTRUM_CLUSTER(uint64_t, 64, 15, 4, 8, 1, 2),
 };
 const SpectrumVariant *spectrum_variants(int *count) {
     *count = (int)(sizeof(kVariants) / sizeof(kVariants[0]));

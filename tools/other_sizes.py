@@ -34,9 +34,25 @@ for n, q, psi in BIG:
     e1.record()
     torch.cuda.synchronize()
     per_s = rows / (e0.elapsed_time(e1) / 10 * 1e-3)
-    print(json.dumps({"n": n, "q_bits": q.bit_length(), "word": plan.word_bytes, "rows": rows, "polymul_per_s": per_s,
-                      "polymul_GBps": per_s * 3 * n * plan.word_bytes / 1e9,
-                      "kernel": dict(plan.variants())[plan.default_variant].split()[0]}), flush=True)
+    out = {"n": n, "q_bits": q.bit_length(), "word": plan.word_bytes, "rows": rows, "polymul_per_s": per_s,
+           "polymul_GBps": per_s * 3 * n * plan.word_bytes / 1e9,
+           "kernel": dict(plan.variants())[plan.default_variant].split()[0]}
+    if plan.spectrum:
+        spec = tntt.forward_spectrum(plan, b)
+        for name, fn in (("forward_spectrum_rows_per_s", lambda: tntt.forward_spectrum(plan, a, out=c)),
+                         ("inverse_spectrum_rows_per_s", lambda: tntt.inverse_spectrum(plan, spec, out=c)),
+                         ("polymul_spectrum_per_s", lambda: tntt.polymul_spectrum(plan, a, spec, out=c))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = rows / (e0.elapsed_time(e1) / 10 * 1e-3)
+        del spec
+    print(json.dumps(out), flush=True)
     del a, b, c
     torch.cuda.empty_cache()
 
