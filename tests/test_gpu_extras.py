@@ -347,3 +347,16 @@ def test_rows_longer_than_one_cta_run_on_clusters(wb, logn, red):
     omega = psi * psi % q
     assert (host(tntt.forward(plan, ta[:2])) == co.cg_ntt(a[:2], omega, q)).all()
     assert sorted(host(sa)[0].tolist()) == sorted(host(tntt.forward(plan, ta[:1], twist=True))[0].tolist())
+
+
+def test_plain_c_client_of_the_transform_domain_entry_points(tmp_path):
+    """examples/cached_operand_driver.c: one key transformed once, many products through tntt_polymul_spectrum."""
+    exe = str(tmp_path / "cached_operand")
+    lib = os.path.join(ROOT, "tiny-ntt_b200")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"),
+                           os.path.join(ROOT, "examples", "cached_operand_driver.c"), "-L" + lib, "-ltntt",
+                           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "PASS" in out.stdout
