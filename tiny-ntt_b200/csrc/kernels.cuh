@@ -783,6 +783,15 @@ __device__ __forceinline__ unsigned cluster_ctarank() {
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Distributed shared memory of a peer CTA may only be touched once that CTA has started executing.  Every CTA
+// arrives on the cluster barrier at kernel entry (cluster_entry_arrive) and waits for its peers' arrivals just
+// before its first remote store (cluster_entry_wait); the wait hides behind the row load and the first pass.
+__device__ __forceinline__ void cluster_entry_arrive() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_entry_wait() {
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 template <typename W> __device__ __forceinline__ void st_cluster(unsigned local_saddr, unsigned rank, W v) {
     unsigned remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_saddr), "r"(rank));
@@ -852,11 +861,13 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
     if (batch) return;   // what-if only: launch overhead calibration
 #endif
 
+    cluster_entry_arrive();
     W x[1][C::R], fa[C::R];
     prefetch_post<C>(gtid, tb.post);
     row_load<C>(x[0], a + off, gtid, active);
     row_load<C>(fa, b + off, gtid, active);                      // b's latency overlaps a's transform
     fwd_pass<C, 0, 1, RED>(x, gtid, tb, mod);
+    cluster_entry_wait();                                        // every peer CTA is running: its shared memory may be written
     cluster_forward_rest<C, CS, RED, PRELOAD, 0>(x, tiles, gtid, tb, mod);
 #pragma unroll
     for (int k = 0; k < C::R; ++k) { const W t = x[0][k]; x[0][k] = fa[k]; fa[k] = t; }
@@ -894,10 +905,12 @@ spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W
     const bool active = row < batch;
     const size_t off = active ? row * C::N : 0;
     constexpr int NX = C::NPASS - 1;
+    cluster_entry_arrive();                                      // see polymul_cluster_kernel
     W fa[C::R];
     if constexpr (MODE == 2) {
         row_load<C>(fa, a + off, gtid, active);
         dit_pass<C, 0, RED, 1>(fa, gtid, tb.inv, mod);
+        cluster_entry_wait();
         cluster_inverse_rest<C, CS, RED, true, 1, 0>(fa, tiles, gtid, tb.inv, mod);
         row_store_scaled<C, 1>(fa, c + off, gtid, active, post, Tw<W>{0, 0}, mod);
     } else {
@@ -909,6 +922,7 @@ spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W
         }
         row_load<C>(x[0], a + off, gtid, active);
         fwd_pass<C, 0, 1, RED>(x, gtid, tb, mod);
+        cluster_entry_wait();
         cluster_forward_rest<C, CS, RED, true, 0>(x, tiles, gtid, tb, mod);
         if constexpr (MODE == 1) {
 #pragma unroll
