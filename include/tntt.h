@@ -73,6 +73,8 @@ typedef struct tntt_plan_info {
     int cluster_variant, cluster_batch_max;
     int small_variant, small_batch_max;
     int spectrum;              /* 1: tntt_spectrum_forward / _inverse / tntt_polymul_spectrum are available */
+    int solinas;               /* 1: q = 2^60 - 2^14 + 1 (rtl/ntt_poly_mult.sv:16-26): the fused kernels may use its
+                                * shift-and-add reductions (variants "red2") instead of the generic lazy ones */
 } tntt_plan_info;
 
 /* Ring parameters N, Q of new_reference/cg_ntt.py:5-6 plus the root the caller passes to

@@ -24,6 +24,12 @@ def lib():
         L.emu_polymul.argtypes = [C.c_int] * 6 + [C.c_void_p] * 3 + [C.c_size_t, C.c_uint64, C.c_uint64]
         L.emu_transform.argtypes = [C.c_int] * 5 + [C.c_void_p] * 2 + [C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.emu_slot.argtypes = [C.c_int] * 7
+        L.emu_polymul_ex.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3 + [C.c_size_t, C.c_uint64, C.c_uint64]
+        L.emu_slot_ex.argtypes = [C.c_int] * 8
+        L.emu_solinas_reduce.argtypes = [C.c_uint64]
+        L.emu_solinas_reduce.restype = C.c_uint64
+        L.emu_solinas_mul.argtypes = [C.c_uint64] * 2
+        L.emu_solinas_mul.restype = C.c_uint64
         L.emu_spectrum.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_size_t, C.c_uint64, C.c_uint64, C.c_int]
         for name, t in (("emu_shoup64", C.c_uint64), ("emu_shoup_lazy64", C.c_uint64), ("emu_mont64", C.c_uint64), ("emu_barrett64", C.c_uint64),
                         ("emu_csub_top64", C.c_uint64), ("emu_shoup32", C.c_uint32), ("emu_mont32", C.c_uint32),
@@ -39,12 +45,13 @@ def lib():
     return _lib
 
 
-def polymul(wb, logn, logr, ppc, na, red, a, b, q, psi):
+def polymul(wb, logn, logr, ppc, na, red, a, b, q, psi, pad=0):
+    """red: 0 / 1 / 2 (Solinas reductions, q = 2^60 - 2^14 + 1 only); pad = 1: padded tile instead of the XOR swizzle"""
     dt = np.uint32 if wb == 4 else np.uint64
     a = np.ascontiguousarray(a, dtype=dt)
     b = np.ascontiguousarray(b, dtype=dt)
     c = np.zeros_like(a)
-    rc = lib().emu_polymul(wb, logn, logr, ppc, na, red, a.ctypes.data, b.ctypes.data, c.ctypes.data, a.size >> logn, q, psi)
+    rc = lib().emu_polymul_ex(wb, logn, logr, ppc, na, red, pad, a.ctypes.data, b.ctypes.data, c.ctypes.data, a.size >> logn, q, psi)
     if rc:
         raise RuntimeError(f"emu_polymul rc={rc}")
     return c

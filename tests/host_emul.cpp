@@ -20,7 +20,7 @@ namespace tntt { long long g_range_violations = 0; }
 
 namespace {
 
-template <class C, int NA, bool RED> struct Emu {
+template <class C, int NA, int RED> struct Emu {
     using W = typename C::W;
     static constexpr int T = C::THREADS;
     std::vector<W> tile;
@@ -37,7 +37,7 @@ template <class C, int NA, bool RED> struct Emu {
         if constexpr (PASS < C::NPASS) {
             if constexpr (PASS > 0) {
                 for (int a = 0; a < NA; ++a) {
-                    W *tl = tile.data() + (size_t)a * C::PPC * C::N;
+                    W *tl = tile.data() + (size_t)a * C::TILE;
                     for (int t = 0; t < T; ++t)
                         tile_write<C, C::fwd_lo(PASS - 1)>(X(t)[a], tl, t >> C::LOGP, t & (C::P - 1));
                     for (int t = 0; t < T; ++t) {
@@ -64,7 +64,7 @@ template <class C, int NA, bool RED> struct Emu {
     }
 
     void polymul(const W *a, const W *b, W *c, size_t batch) {
-        tile.assign((size_t)NA * C::PPC * C::N, 0);
+        tile.assign((size_t)NA * C::TILE, 0);
         x.assign((size_t)T * NA * C::R, 0);
         fa.assign((size_t)T * C::R, 0);
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
@@ -83,9 +83,7 @@ template <class C, int NA, bool RED> struct Emu {
                 forward_from<0>();
                 for (int t = 0; t < T; ++t)
                     for (int k = 0; k < C::R; ++k) {
-                        W u = F(t)[k];
-                        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
-                        F(t)[k] = mont_mul(u, X(t)[0][k], mod);
+                        F(t)[k] = pointwise_product<C, RED>(F(t)[k], X(t)[0][k], mod);
                     }
             } else {
                 for (int t = 0; t < T; ++t) {
@@ -96,9 +94,7 @@ template <class C, int NA, bool RED> struct Emu {
                 forward_from<0>();
                 for (int t = 0; t < T; ++t)
                     for (int k = 0; k < C::R; ++k) {
-                        W u = X(t)[0][k];
-                        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
-                        F(t)[k] = mont_mul(u, X(t)[NA - 1][k], mod);
+                        F(t)[k] = pointwise_product<C, RED>(X(t)[0][k], X(t)[NA - 1][k], mod);
                     }
             }
             dit_from<pointwise_out_bound<C, RED>(), 0>(tb.inv);
@@ -111,7 +107,7 @@ template <class C, int NA, bool RED> struct Emu {
 
     // transform-domain kernels (spectrum_forward_kernel / spectrum_inverse_kernel / polymul_spectrum_kernel)
     void spectrum_forward(const W *in, W *out, size_t batch, bool natural = false) {
-        tile.assign((size_t)C::PPC * C::N, 0);
+        tile.assign((size_t)C::TILE, 0);
         x.assign((size_t)T * NA * C::R, 0);
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
         for (size_t cta = 0; cta < ctas; ++cta) {
@@ -132,7 +128,7 @@ template <class C, int NA, bool RED> struct Emu {
         }
     }
     void spectrum_inverse(const W *in, W *out, size_t batch, const Tw<W> *post, bool natural = false, Tw<W> uniform = Tw<W>{0, 0}) {
-        tile.assign((size_t)C::PPC * C::N, 0);
+        tile.assign((size_t)C::TILE, 0);
         fa.assign((size_t)T * C::R, 0);
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
         for (size_t cta = 0; cta < ctas; ++cta) {
@@ -152,7 +148,7 @@ template <class C, int NA, bool RED> struct Emu {
         }
     }
     void polymul_spectrum(const W *a, const W *bspec, W *c, size_t batch, size_t b_stride) {
-        tile.assign((size_t)C::PPC * C::N, 0);
+        tile.assign((size_t)C::TILE, 0);
         x.assign((size_t)T * NA * C::R, 0);
         fa.assign((size_t)T * C::R, 0);
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
@@ -166,9 +162,7 @@ template <class C, int NA, bool RED> struct Emu {
                 const size_t poly = cta * C::PPC + (t >> C::LOGP);
                 const W *brow = bspec + (poly < batch ? poly * b_stride : 0);
                 for (int k = 0; k < C::R; ++k) {
-                    W u = X(t)[0][k];
-                    if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
-                    F(t)[k] = mont_mul(u, brow[(k << C::LOGP) + (t & (C::P - 1))], mod);
+                    F(t)[k] = pointwise_product<C, RED>(X(t)[0][k], brow[(k << C::LOGP) + (t & (C::P - 1))], mod);
                 }
             }
             dit_from<2, 0>(tb.inv);
@@ -181,7 +175,7 @@ template <class C, int NA, bool RED> struct Emu {
 
     // standalone transform kernel body (transform_kernel in kernels.cuh)
     void transform(const W *in, W *out, size_t batch, const TransformTables<W> &tt) {
-        tile.assign((size_t)C::PPC * C::N, 0);
+        tile.assign((size_t)C::TILE, 0);
         fa.assign((size_t)T * C::R, 0);
         const size_t ctas = (batch + C::PPC - 1) / C::PPC;
         for (size_t cta = 0; cta < ctas; ++cta) {
@@ -210,16 +204,19 @@ template <class C, int NA, bool RED> struct Emu {
     }
 };
 
-template <class C, int NA, bool RED>
+template <class C, int NA, int RED>
 int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q, uint64_t psi) {
     using W = typename C::W;
     constexpr int BITS = WordTraits<W>::BITS;
     if (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN)) return -2;
+    if (RED == 2 && q != kSolinasQ) return -2;
     const uint64_t omega = host::mulmod(psi, psi, q);
     auto fwd = host::fwd_pyramid<W>(psi, C::N, q);
     auto last = host::fwd_last_table<W>(fwd, C::LOGN, C::LOGR);
     auto inv = host::dit_pyramid<W>(host::modinv(omega, q), C::N, q);
-    const uint64_t scale = host::mulmod(host::modinv(C::N % q, q), (uint64_t)((((host::u128)1) << BITS) % q), q);
+    // the Montgomery pointwise product (red 0/1) leaves a factor 2^-BITS for the store table to undo; the Solinas one does not
+    const uint64_t scale = RED == 2 ? host::modinv(C::N % q, q)
+                                    : host::mulmod(host::modinv(C::N % q, q), (uint64_t)((((host::u128)1) << BITS) % q), q);
     auto post = host::scaled_powers<W>(host::modinv(psi, q), scale, C::N, q);
     Emu<C, NA, RED> e;
     e.tb.fwd_pyr = fwd.data();
@@ -301,9 +298,10 @@ int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t 
 
 }  // namespace
 
-#define POLY_CASE(WB, WT, LN, LR, PPC, NA_, RED_)                                                      \
-    if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && na == NA_ && red == RED_)       \
-        return run_polymul<Cfg<WT, LN, LR, PPC>, NA_, (RED_ != 0)>(a, b, c, batch, q, psi);
+#define POLY_CASE(WB, WT, LN, LR, PPC, NA_, RED_) POLY_CASE_P(WB, WT, LN, LR, PPC, NA_, RED_, 0)
+#define POLY_CASE_P(WB, WT, LN, LR, PPC, NA_, RED_, PAD_)                                              \
+    if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && na == NA_ && red == RED_ && pad == PAD_) \
+        return run_polymul<Cfg<WT, LN, LR, PPC, PAD_>, NA_, RED_>(a, b, c, batch, q, psi);
 #define XFORM_CASE(WB, WT, LN, LR, PPC, RED_)                                                          \
     if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && red == RED_)                    \
         return run_transform<Cfg<WT, LN, LR, PPC>, (RED_ != 0)>(in, out, batch, q, root, mode, reduce_input);
@@ -338,8 +336,18 @@ int emu_spectrum(int word_bytes, int logn, int logr, int ppc, int red, const voi
     return -1;
 }
 
-int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, const void *a, const void *b, void *c,
-                size_t batch, uint64_t q, uint64_t psi) {
+// red: 0 / 1 / 2 (Solinas, q = 2^60 - 2^14 + 1 only); pad: 1 = padded tile
+int emu_polymul_ex(int word_bytes, int logn, int logr, int ppc, int na, int red, int pad, const void *a, const void *b, void *c,
+                   size_t batch, uint64_t q, uint64_t psi) {
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 1, 1, 1)
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 2, 1, 1)
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 1, 2, 0)
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 2, 2, 0)
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 1, 2, 1)
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 2, 2, 1)
+    POLY_CASE_P(8, uint64_t, 8, 4, 16, 1, 2, 0)     // small Solinas shapes: quick exhaustive-ish tests
+    POLY_CASE_P(8, uint64_t, 8, 4, 16, 1, 1, 1)
+    POLY_CASE_P(8, uint64_t, 10, 4, 4, 1, 2, 1)
     POLY_CASE(4, uint32_t, 2, 1, 2, 1, 0)
     POLY_CASE(4, uint32_t, 4, 2, 4, 1, 0)
     POLY_CASE(4, uint32_t, 5, 2, 2, 2, 0)
@@ -377,6 +385,11 @@ int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, co
     return -1;
 }
 
+int emu_polymul(int word_bytes, int logn, int logr, int ppc, int na, int red, const void *a, const void *b, void *c,
+                size_t batch, uint64_t q, uint64_t psi) {
+    return emu_polymul_ex(word_bytes, logn, logr, ppc, na, red, 0, a, b, c, batch, q, psi);
+}
+
 int emu_transform(int word_bytes, int logn, int logr, int ppc, int red, const void *in, void *out, size_t batch,
                   uint64_t q, uint64_t root, int mode, int reduce_input) {
     XFORM_CASE(4, uint32_t, 4, 2, 4, 0)
@@ -392,13 +405,17 @@ int emu_transform(int word_bytes, int logn, int logr, int ppc, int red, const vo
 }
 
 // shared-memory slot of (poly-in-cta, register k, thread tid) for a register field at bit `lo`
-int emu_slot(int word_bytes, int logn, int logr, int lo, int pl, int tid, int k) {
+int emu_slot_ex(int word_bytes, int logn, int logr, int lo, int pl, int tid, int k, int pad) {
     const int n = 1 << logn;
     const int e = ((tid >> lo) << (lo + logr)) | (k << lo) | (tid & ((1 << lo) - 1));
     const int E = pl * n + e;
+    if (pad) return E + (E >> 4);   // Cfg::spos, PAD = 1
     const int mask = (1 << (word_bytes == 4 ? 5 : 4)) - 1;
     return E ^ ((E >> logr) & mask);
 }
+int emu_slot(int word_bytes, int logn, int logr, int lo, int pl, int tid, int k) { return emu_slot_ex(word_bytes, logn, logr, lo, pl, tid, k, 0); }
+uint64_t emu_solinas_reduce(uint64_t x) { return solinas_reduce(x); }
+uint64_t emu_solinas_mul(uint64_t u, uint64_t v) { return solinas_mul(u, v); }
 
 // arithmetic probes for tests/test_modarith.py
 uint64_t emu_shoup64(uint64_t x, uint64_t w, uint64_t q) { auto t = host::make_tw<uint64_t>(w, q); return shoup_mul(x, t.w, t.wp, (uint64_t)(0 - q)); }

@@ -253,3 +253,51 @@ def test_emulated_kernels_at_the_largest_modulus_each_path_accepts(wb, logn, log
         assert (emu.spectrum(wb, logn, logr, ppc, red, a, b, q, psi, 0).astype(np.uint64) == a).all(), q
         assert (emu.spectrum(wb, logn, logr, ppc, red, a, a, q, psi, 7).astype(np.uint64) == co.cg_intt(a, psi * psi % q, q)).all(), q
         assert emu.lib().emu_range_violations() == 0, q
+
+
+# round 2: padded tile (pad) and the Solinas-form reductions (red 2) of the N = 4096 / 60-bit shapes
+SOLINAS_Q = (1 << 60) - (1 << 14) + 1
+
+
+@pytest.mark.parametrize("na,red,pad", [(2, 1, 1), (2, 2, 1), (1, 2, 0), (2, 2, 0), (1, 1, 1), (1, 2, 1)])
+def test_emulated_padded_and_solinas_shapes(na, red, pad, co):
+    p = O.PARAMS["n4096_60"]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    assert q == SOLINAS_Q
+    rng = np.random.default_rng(na * 100 + red * 10 + pad)
+    a = rng.integers(0, q, size=(4, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(4, n), dtype=np.uint64)
+    a[0], b[0] = O.make_poly("n4096_60", 1), O.make_poly("n4096_60", 2)
+    a[1], b[1] = q - 1, q - 1          # largest canonical values: worst case for the lazy ranges
+    a[2], b[2] = 0, q - 1
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    got = emu.polymul(8, 12, 4, 1, na, red, a, b, q, psi, pad=pad).astype(np.uint64)
+    assert (got == want).all()
+    assert emu.lib().emu_range_violations() == 0
+
+
+def test_solinas_shapes_refuse_other_moduli():
+    # red 2 is written for one modulus; the emulation (like tntt_variant_matches) refuses every other
+    q = emu.largest_friendly_prime(4096, lambda v: v < SOLINAS_Q)
+    assert q != SOLINAS_Q and q % 8192 == 1
+    a = np.zeros((1, 4096), dtype=np.uint64)
+    with pytest.raises(RuntimeError):
+        emu.polymul(8, 12, 4, 1, 2, 2, a, a, q, 3, pad=1)
+
+
+def test_solinas_arithmetic_primitives():
+    L = emu.lib()
+    q = SOLINAS_Q
+    rnd = random.Random(5)
+    edge = [0, 1, q - 1, q, q + 1, 2 * q, (1 << 60) - 1, 1 << 60, (1 << 64) - 1, (1 << 64) - q, 15 * q + 12345]
+    for x in edge + [rnd.getrandbits(64) for _ in range(20000)]:
+        r = L.emu_solinas_reduce(x)
+        assert r % q == x % q and r < q + (1 << 18)          # "below two units" of the bound tracker
+    for _ in range(20000):
+        u, v = rnd.getrandbits(64), rnd.getrandbits(64)
+        r = L.emu_solinas_mul(u, v)
+        assert r % q == u * v % q and r < (1 << 60) + (1 << 37)
+    for u in edge:
+        for v in edge:
+            r = L.emu_solinas_mul(u, v)
+            assert r % q == u * v % q and r < (1 << 60) + (1 << 37)

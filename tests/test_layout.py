@@ -52,3 +52,41 @@ def test_tile_slot_map_is_a_bijection(wb, logn, logr, ppc, fields):
                 for k in range(1 << logr):
                     seen.add(L.emu_slot(wb, logn, logr, lo, pl, t, k))
         assert seen == set(range(ppc * n))
+
+
+def test_padded_tile_is_conflict_free_and_injective():
+    """Cfg<uint64_t, 12, 4, 1, PAD = 1>: slot = E + (E >> 4) (one pad word per 16)."""
+    L = emu.lib()
+    wb, logn, logr = 8, 12, 4
+    p = 1 << (logn - logr)
+    for lo in (8, 4, 0):
+        seen = set()
+        for warp in range(0, p, 32):
+            for k in range(1 << logr):
+                slots = [L.emu_slot_ex(wb, logn, logr, lo, 0, t, k, 1) for t in range(warp, warp + 32)]
+                assert wavefronts(wb, slots) == 2, (lo, warp, k)
+                seen.update(slots)
+        assert len(seen) == 1 << logn and max(seen) < (1 << logn) + (1 << (logn - 4))
+
+
+@pytest.mark.parametrize("wb,logn,logr,ppc,fields", GEOMS)
+def test_warp_local_exchanges_stay_inside_their_thread_group(wb, logn, logr, ppc, fields):
+    """exchange_is_warp_local() in kernels.cuh: a regrouping between register fields at 0 and at LO <= 5 is ordered by
+    __syncwarp() only.  That is sound iff every tile slot is written (layout A) and read (layout B) by threads of the
+    same aligned group of 2^LO <= 32 consecutive threads -- for both directions and for every polynomial of the CTA."""
+    L = emu.lib()
+    p = 1 << (logn - logr)
+    los = sorted(set(fields))
+    for lo in los:
+        if lo == 0 or lo > 5 or 0 not in los:
+            continue
+        group = 1 << lo
+        owner = {}
+        for layout in (0, lo):
+            for pl in range(ppc):
+                for t in range(p):
+                    for k in range(1 << logr):
+                        s = L.emu_slot(wb, logn, logr, layout, pl, t, k)
+                        g = (pl * p + t) // group
+                        assert owner.setdefault(s, g) == g, (lo, layout, pl, t, k)
+        assert group <= 32 and 32 % group == 0

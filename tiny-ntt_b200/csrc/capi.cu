@@ -154,6 +154,7 @@ template <typename W> int build_tables(tntt_plan *p) {
 int choose_default_variant(const tntt_plan *p) {
     // preference order measured on B200 (profiles/): first match wins
     static const char *prefer[] = {
+        "u64_n12_r4_p1_a2_red2_b2_s0_t0_pad", "u64_n12_r4_p1_a2_red1_b2_s0_t0_pad",
         "u64_n12_r4_p1_a1_red1_b3_s1_t0", "u64_n12_r4_p1_a2_red1_b2_s0_t0", "u64_n12_r4_p1_a1_red0_b2_s0_t0",
         "u32_n12_r4_p1_a2_red0_b3_s0_t0", "u32_n10_r5_p8_a2_red0_b2_s0_t0", "u32_n8_r4_p16_a2_red0_b3_s0_t0",
     };
@@ -243,6 +244,7 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
     // uint32 coefficients when the whole transform fits the lazy 32-bit range, else uint64
     I.word_bytes = host::lazy_full_ok<uint32_t>(q, (int)I.logn) ? 4 : 8;
     I.lazy_reduce = (I.word_bytes == 8 && !host::lazy_full_ok<uint64_t>(q, (int)I.logn)) ? 1 : 0;
+    I.solinas = (q == kSolinasQ) ? 1 : 0;
     p->mod32 = host::make_mod<uint32_t>(q < (1ull << 32) ? q : 3, (int)I.logn);
     p->mod64 = host::make_mod<uint64_t>(q, (int)I.logn);
     I.barrett_k = p->mod64.k;
@@ -386,7 +388,8 @@ template <typename W> int launch_variant(const tntt_plan *p, const PolymulVarian
     PolymulTables<W> tb;
     tb.fwd_pyr = (const Tw<W> *)p->fwd_pyr;
     tb.fwd_last = (const Tw<W> *)p->fwd_last[v.logr];
-    tb.post = (const Tw<W> *)p->post_mont;
+    // the Montgomery pointwise product of red 0/1 leaves a factor 2^-BITS for the store table to undo; the Solinas one does not
+    tb.post = (const Tw<W> *)(v.red == 2 ? p->post_untwist : p->post_mont);
     tb.inv.pyr = (const Tw<W> *)p->inv_pyr;
     if constexpr (sizeof(W) == 4) { memcpy(tb.fwd_head, p->head32[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head32[1], sizeof tb.inv.head); }
     else { memcpy(tb.fwd_head, p->head64[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head64[1], sizeof tb.inv.head); }
@@ -570,7 +573,8 @@ int tntt_variant_matches(const tntt_plan *p, int variant) {
     if (!p || variant < 0 || variant >= tntt_variant_count()) return 0;
     const PolymulVariant &v = all_variants()[variant];
     if (!p->info.has_psi || v.word_bytes != p->info.word_bytes || v.logn != (int)p->info.logn) return 0;
-    if (v.red != p->info.lazy_reduce) return 0;
+    // red 2 = the Solinas-form reductions: an alternative to red 1 for the one modulus they are written for
+    if (v.red == 2 ? !(p->info.lazy_reduce && p->info.solinas) : v.red != p->info.lazy_reduce) return 0;
     if (v.red && !host::lazy_pass_ok<uint64_t>(p->info.q, v.logr)) return 0;
     return 1;
 }

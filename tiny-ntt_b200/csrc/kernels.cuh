@@ -25,12 +25,17 @@
 #pragma once
 #include "modarith.cuh"
 
-// how many twiddles (TNTT_TG) / store-table entries (TNTT_POST_GROUP) are fetched ahead of their use
-#ifndef TNTT_TG
-#define TNTT_TG 4
+// how many twiddles (TG) / store-table entries (POST_GROUP) are fetched ahead of their use: Cfg::TG / Cfg::POST_GROUP
+// (measured per shape on B200, profiles/r02_whatif_*.log); -DTNTT_TG / -DTNTT_POST_GROUP override them for experiments
+#ifdef TNTT_TG
+constexpr int kTgOverride = TNTT_TG;
+#else
+constexpr int kTgOverride = 0;
 #endif
-#ifndef TNTT_POST_GROUP
-#define TNTT_POST_GROUP 4
+#ifdef TNTT_POST_GROUP
+constexpr int kPostGroupOverride = TNTT_POST_GROUP;
+#else
+constexpr int kPostGroupOverride = 0;
 #endif
 
 namespace tntt {
@@ -45,13 +50,26 @@ TNTT_CX int cbitrev(int v, int bits) {   // compile-time bit reversal (register 
 
 // Geometry of one kernel variant: W word, N = 2^LOGN coefficients, R = 2^LOGR per thread,
 // PPC polynomials per CTA, NA operands transformed side by side (sharing twiddle loads).
-template <typename W_, int LOGN_, int LOGR_, int PPC_> struct Cfg {
+// PAD_ = 1 (64-bit words, 16 coefficients per thread): the tile is padded by one word per 16 instead of XOR-swizzled.
+// Slots are then linear in the register index, so an exchange needs one base address per access pattern and
+// immediate offsets (the swizzle costs a LOP3 + LEA per access); still conflict-free for every pattern used.
+template <typename W_, int LOGN_, int LOGR_, int PPC_, int PAD_ = 0> struct Cfg {
     using W = W_;
+    static constexpr int PAD = PAD_;
     static constexpr int LOGN = LOGN_, LOGR = LOGR_, N = 1 << LOGN, R = 1 << LOGR;
     static constexpr int LOGP = LOGN - LOGR, P = 1 << LOGP;  // threads per polynomial
     static constexpr int PPC = PPC_, THREADS = P * PPC;
     static constexpr int NPASS = (LOGN + LOGR - 1) / LOGR;
     static constexpr int BANK_MASK = (1 << WordTraits<W>::BANK_BITS) - 1;
+    // the padded shapes run two operands side by side at 128 registers: deeper twiddle groups, shallower store groups
+    static constexpr int TG = kTgOverride ? kTgOverride : (PAD_ ? 8 : 4);
+    static constexpr int POST_GROUP = kPostGroupOverride ? kPostGroupOverride : (PAD_ ? 2 : 4);
+    // NA > 1: both operands' CTA-wide regroupings share one pair of barriers (measured: only pays in the padded shapes)
+#ifdef TNTT_MERGE_EXCH
+    static constexpr int MERGE_EXCH = TNTT_MERGE_EXCH;   // bit 0: the warp-local exchanges, bit 1: the CTA-wide ones
+#else
+    static constexpr int MERGE_EXCH = PAD_ ? 2 : 0;
+#endif
     // per-thread twiddle tables are prefetched one pass ahead only when they are too big to stay in L1
     #if defined(TNTT_FORCE_PREFETCH)
     static constexpr bool PREFETCH = true;
@@ -72,7 +90,12 @@ template <typename W_, int LOGN_, int LOGR_, int PPC_> struct Cfg {
         return ((tid >> LO) << (LO + LOGR)) | (k << LO) | (tid & ((1 << LO) - 1));
     }
     // shared-memory slot of CTA-wide element index E (= poly_in_cta * N + coefficient index)
-    static TNTT_HD int spos(int E) { return E ^ ((E >> LOGR) & BANK_MASK); }
+    static constexpr int TILE = PPC * N + (PAD ? PPC * N / 16 : 0);   // words of one tile
+    static_assert(!PAD || (sizeof(W_) == 8 && LOGR_ == 4), "the padded tile is laid out for 8-byte words, R = 16");
+    static TNTT_HD int spos(int E) {
+        if constexpr (PAD) return E + (E >> 4);
+        else return E ^ ((E >> LOGR) & BANK_MASK);
+    }
     // size of the transposed last-forward-pass twiddle table
     static constexpr int FWD_LAST_ENTRIES = (R - 1) * P;
 };
@@ -159,10 +182,13 @@ template <typename W> TNTT_HD void st_stream(W *p, W v) {
 // Lazy reduction before a stage: only the registers that enter it as the un-multiplied ("x") input
 // need it -- the other input goes through shoup_mul(), which accepts
 // any word, and every later stage inherits bound(x) + 2q.  KB = register-index bit of that stage.
-template <class C, int KB> TNTT_HD void reduce_top_x(typename C::W (&x)[C::R], const Mod<typename C::W> &mod) {
+template <class C, int KB, int RED> TNTT_HD void reduce_top_x(typename C::W (&x)[C::R], const Mod<typename C::W> &mod) {
 #pragma unroll
     for (int k = 0; k < C::R; ++k)
-        if (!(k & (1 << KB))) x[k] = csub_top(x[k], mod.top_sub);
+        if (!(k & (1 << KB))) {
+            if constexpr (RED == 2) x[k] = solinas_reduce(x[k]);
+            else x[k] = csub_top(x[k], mod.top_sub);
+        }
 }
 
 // twiddle pair from a shared-memory copy of a table (filled by a TMA bulk copy, see polymul_kernel)
@@ -189,7 +215,7 @@ template <typename W> TNTT_HD Tw<W> ld_tw_shared(const Tw<W> *p) {
 // PRE: the twiddle of the pass's first stage was loaded before the tile exchange (pre_t), so its
 // latency overlaps the barriers instead of following them
 // ALLPRE: all R-1 twiddles of the pass were loaded beforehand into pre_t[slot] (fwd_load_pass_twiddles)
-template <class C, int PASS, int NA, bool RED, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
+template <class C, int PASS, int NA, int RED, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                        const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr,
                        const Tw<typename C::W> *pre_t = nullptr) {
@@ -200,10 +226,10 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
     constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
     if constexpr (stage_needs_reduction(RED, Growth<W>::G, bound_at(RED, Growth<W>::G, 1, s))) {
 #pragma unroll
-        for (int a = 0; a < NA; ++a) reduce_top_x<C, kb>(x[a], mod);
+        for (int a = 0; a < NA; ++a) reduce_top_x<C, kb, RED>(x[a], mod);
     }
     // twiddles are fetched TG at a time, ahead of their butterflies, so that their latencies overlap
-    constexpr int TG = NG < TNTT_TG ? NG : TNTT_TG;
+    constexpr int TG = NG < C::TG ? NG : C::TG;
 #pragma unroll
     for (int g0 = 0; g0 < NG; g0 += TG) {
         Tw<W> tw[TG];
@@ -282,27 +308,37 @@ template <class C> TNTT_HD void prefetch_post(int tid, const Tw<typename C::W> *
     for (int k = 0; k < C::R; ++k) prefetch_l1(&post[(k << C::LOGP) + tid]);
 }
 
-template <class C, int PASS, int NA, bool RED, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
+template <class C, int PASS, int NA, int RED, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void fwd_pass(typename C::W (&x)[NA][C::R], int tid, const PolymulTables<typename C::W> &tb,
                       const Mod<typename C::W> &mod, const Tw<typename C::W> *stab = nullptr,
                       const Tw<typename C::W> *pre_t = nullptr) {
     fwd_stage<C, PASS, NA, RED, C::fwd_bhi(PASS) - 1, SMEM_TW, PRE, ALLPRE>(x, tid, tb, mod, stab, pre_t);
 }
 // bound (units of 2^(BITS-4)) of the spectrum a forward transform of canonical input leaves in registers
-template <class C, bool RED> TNTT_CX int fwd_out_bound() {
+template <class C, int RED> TNTT_CX int fwd_out_bound() {
     return bound_at(RED, Growth<typename C::W>::G, 1, C::LOGN);
 }
-// ... and of the Montgomery product of a top-reduced u with such a v:  u*v/2^BITS + q
-template <class C, bool RED> TNTT_CX int pointwise_out_bound() {
+// ... and of the pointwise product of two such spectra: Montgomery (red 0/1; u top-reduced first) u*v/2^BITS + q,
+// Solinas (red 2) below 2 q
+template <class C, int RED> TNTT_CX int pointwise_out_bound() {
+    if (RED == 2) return 2;
     constexpr int bf = fwd_out_bound<C, RED>();
     return ((bf > 8 ? 8 : bf) * bf + 15) / 16 + 1;
+}
+// rtl/ntt_pointwise_mult.v:17-42 on the registers of one thread: u, v = lazy spectra of a and b
+template <class C, int RED> TNTT_HD typename C::W pointwise_product(typename C::W u, typename C::W v, const Mod<typename C::W> &mod) {
+    if constexpr (RED == 2) return solinas_mul(u, v);
+    else {
+        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);  // u < 2^(BITS-1): no overflow
+        return mont_mul(u, v, mod);   // the 2^-BITS is undone by the store table
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
 // ---------------------------------------------------------------------------------------------
 // IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
-template <class C, int PASS, bool RED, int IN_BND, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
+template <class C, int PASS, int RED, int IN_BND, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
                        const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
     using W = typename C::W;
@@ -311,11 +347,11 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
     constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
     if constexpr (B == 0 && dit_trivial_ok(RED, IN_BND)) {   // twiddle 1: no product at all
 #pragma unroll
-        for (int g = 0; g < NG; ++g) trivial_butterfly(x[2 * g], x[2 * g + 1], mod);
+        for (int g = 0; g < NG; ++g) trivial_butterfly(x[2 * g], x[2 * g + 1], RED == 2 ? mod.q2 : mod.triv_c);
     } else {
     if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
-        reduce_top_x<C, kb>(x, mod);
-    constexpr int TG = NJ < TNTT_TG ? NJ : TNTT_TG;
+        reduce_top_x<C, kb, RED>(x, mod);
+    constexpr int TG = NJ < C::TG ? NJ : C::TG;
 #pragma unroll
     for (int j0 = 0; j0 < NJ; j0 += TG) {
         Tw<W> tw[TG];
@@ -342,7 +378,7 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
     }
     if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1, SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
 }
-template <class C, int PASS, bool RED, int IN_BND, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
+template <class C, int PASS, int RED, int IN_BND, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
 TNTT_HD void dit_pass(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
                       const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
     dit_stage<C, PASS, RED, IN_BND, C::inv_blo(PASS), SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
@@ -397,7 +433,7 @@ template <class C> TNTT_HD void row_load(typename C::W (&x)[C::R], const typenam
 // final multiply (psi^-i N^-1 ...) + canonical reduction + coalesced store.
 // TABLE: 1 = per-coefficient table `post` (loaded GROUP entries at a time so that their L2 latencies
 // overlap instead of one exposed load per coefficient), 0 = one uniform factor, -1 = decided at run time.
-template <class C, int TABLE = -1, int GROUP_ = TNTT_POST_GROUP>
+template <class C, int TABLE = -1, int GROUP_ = C::POST_GROUP>
 TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row, int tid, bool active,
                               const Tw<typename C::W> *post, const Tw<typename C::W> &post_uniform,
                               const Mod<typename C::W> &mod) {
@@ -411,7 +447,11 @@ TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row
             for (int j = 0; j < GROUP; ++j) t[j] = ld_tw(&post[((k0 + j) << C::LOGP) + tid]);
 #pragma unroll
             for (int j = 0; j < GROUP; ++j) {
+#if defined(TNTT_X_NO_POST)
+                const W v = x[k0 + j] ^ t[j].w;   // what-if only
+#else
                 const W v = csub(shoup_mul(x[k0 + j], t[j].w, t[j].wp, mod.nq), mod.q);
+#endif
                 if (active) st_stream(row + ((k0 + j) << C::LOGP) + tid, v);
             }
         }
@@ -437,14 +477,30 @@ template <class C> __device__ __forceinline__ void tile_sync() {
     if constexpr (C::P <= 32) __syncwarp();
     else __syncthreads();
 }
+// A regrouping between the layouts LO_A and LO_B with min = 0 only moves coefficients among the 2^max aligned,
+// consecutive threads that share tid >> max (they hold the same 2^(max + LOGR) consecutive coefficients before and
+// after), and nobody else touches that part of the tile in either layout.  When such a group sits inside one warp
+// the exchange needs a warp barrier only, and the warps of the CTA are free to drift apart (test_layout.py
+// enumerates the thread sets).
+template <class C, int LO_A, int LO_B> TNTT_CX bool exchange_is_warp_local() {
+#if defined(TNTT_X_CTA_SYNC_ONLY)
+    return C::P <= 32;
+#else
+    return C::P <= 32 || ((LO_A < LO_B ? LO_A : LO_B) == 0 && (LO_A < LO_B ? LO_B : LO_A) <= 5);
+#endif
+}
+template <class C, int LO_A, int LO_B> __device__ __forceinline__ void exchange_sync() {
+    if constexpr (exchange_is_warp_local<C, LO_A, LO_B>()) __syncwarp();
+    else __syncthreads();
+}
 template <class C, int LO_FROM, int LO_TO>
 __device__ __forceinline__ void exchange(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid) {
 #if defined(TNTT_X_NO_EXCHANGE)
     return;   // what-if only: wrong results
 #endif
-    tile_sync<C>();  // everybody is done reading the tile's previous contents
+    exchange_sync<C, LO_FROM, LO_TO>();  // everybody is done reading the tile's previous contents
     tile_write<C, LO_FROM>(x, tile, pl, tid);
-    tile_sync<C>();
+    exchange_sync<C, LO_FROM, LO_TO>();
     tile_read<C, LO_TO>(x, tile, pl, tid);
 }
 
@@ -486,7 +542,7 @@ struct TmaStage {
     }
 };
 
-template <class C, int NA, bool RED, bool TMA, int PASS = 0>
+template <class C, int NA, int RED, bool TMA, int PASS = 0>
 __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typename C::W *tile, int pl, int tid,
                                             const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod,
                                             TmaStage *tma = nullptr, const Tw<typename C::W> *stab = nullptr,
@@ -497,9 +553,21 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
         Tw<typename C::W> t0{};
         if constexpr (PRE) t0 = fwd_first_twiddle<C, PASS>(tid, tb);
         if constexpr (PASS > 0) {
+#if defined(TNTT_X_NO_EXCHANGE)
+            if constexpr (false) {
+#else
+            if constexpr (NA > 1 && ((exchange_is_warp_local<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>() ? 1 : 2) & C::MERGE_EXCH)) {
+                // one pair of barriers serves all operands (each has its own tile)
+#endif
+                exchange_sync<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>();
 #pragma unroll
-            for (int a = 0; a < NA; ++a) {
-                exchange<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[a], tile + a * C::PPC * C::N, pl, tid);
+                for (int a = 0; a < NA; ++a) tile_write<C, C::fwd_lo(PASS - 1)>(x[a], tile + a * C::TILE, pl, tid);
+                exchange_sync<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>();
+#pragma unroll
+                for (int a = 0; a < NA; ++a) tile_read<C, C::fwd_lo(PASS)>(x[a], tile + a * C::TILE, pl, tid);
+            } else {
+#pragma unroll
+                for (int a = 0; a < NA; ++a) exchange<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[a], tile + a * C::TILE, pl, tid);
             }
         }
         if constexpr (PASS + 2 == C::NPASS && C::PREFETCH && !TMA) prefetch_fwd_last<C>(tid, tb);
@@ -512,35 +580,45 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
 }
 
 // PF: prefetch the last pass's twiddles and the store table one pass ahead
-template <class C, bool RED, int IN_BND, bool TMA, bool PF, int PASS = 0>
+template <class C, int RED, int IN_BND, bool TMA, bool PF, int PASS = 0>
 __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W *tile, int pl, int tid,
                                         const DitTables<typename C::W> &dt, const Tw<typename C::W> *post,
                                         const Mod<typename C::W> &mod, TmaStage *tma = nullptr,
                                         const Tw<typename C::W> *stab = nullptr) {
     if constexpr (PASS < C::NPASS) {
-        constexpr bool PRE = PASS > 0 && C::inv_lo(PASS) == C::inv_blo(PASS) && !(TMA && PASS + 1 == C::NPASS);
+#ifndef TNTT_INV_ALLPRE
+#define TNTT_INV_ALLPRE 0
+#endif
+        // APRE: every twiddle of the pass is fetched before the exchange (the inverse of a kernel built for two operands
+        // side by side has the registers of the second operand to spare)
+        constexpr bool APRE = TNTT_INV_ALLPRE && PASS > 0 && !TMA && PF;
+        constexpr bool PRE = !APRE && PASS > 0 && C::inv_lo(PASS) == C::inv_blo(PASS) && !(TMA && PASS + 1 == C::NPASS);
         Tw<typename C::W> t0{};
+        Tw<typename C::W> tall[APRE ? C::R - 1 : 1];
         if constexpr (PRE) t0 = dit_first_twiddle<C, PASS>(tid, dt);
+        if constexpr (APRE) dit_load_pass_twiddles<C, PASS>(tall, tid, dt);
 #if defined(TNTT_X_NO_EXCHANGE)
         if constexpr (false) {
 #else
         if constexpr (PASS > 0) {
 #endif
             if constexpr (TMA) __syncthreads();  // everybody is done reading the tile and, for PASS 1, the forward twiddle buffer
-            else tile_sync<C>();
+            else exchange_sync<C, C::inv_lo(PASS - 1), C::inv_lo(PASS)>();
             if constexpr (TMA && PASS == 1) {
                 constexpr int first = 1 << C::inv_blo(C::NPASS - 1);
                 if (threadIdx.x == 0)
                     tma->issue(dt.pyr + first, (unsigned)((C::N - first) * sizeof(Tw<typename C::W>)));
             }
             tile_write<C, C::inv_lo(PASS - 1)>(x, tile, pl, tid);
-            tile_sync<C>();
+            if constexpr (TMA) __syncthreads();
+            else exchange_sync<C, C::inv_lo(PASS - 1), C::inv_lo(PASS)>();
             tile_read<C, C::inv_lo(PASS)>(x, tile, pl, tid);
         }
         if constexpr (PASS + 2 == C::NPASS && PF && !TMA) prefetch_dit_last<C>(tid, dt.pyr);
         if constexpr (PASS + 1 == C::NPASS && PF) prefetch_post<C>(tid, post);
         if constexpr (TMA && PASS + 1 == C::NPASS) tma->wait();
-        dit_pass<C, PASS, RED, IN_BND, TMA, PRE>(x, tid, dt, mod, stab, &t0);
+        if constexpr (APRE) dit_pass<C, PASS, RED, IN_BND, false, false, true>(x, tid, dt, mod, nullptr, tall);
+        else dit_pass<C, PASS, RED, IN_BND, TMA, PRE>(x, tid, dt, mod, stab, &t0);
         dit_all<C, RED, IN_BND, TMA, PF, PASS + 1>(x, tile, pl, tid, dt, post, mod, tma, stab);
     }
 }
@@ -554,7 +632,7 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
 //   STASH = 1 (NA = 1 only): a's spectrum waits in a second shared tile instead of in registers while
 //              b is transformed (thread-private slots, [k][thread] order: no conflicts, no barrier)
 //   TMA = 1: the per-thread twiddle tables are staged in shared memory by bulk async copies (see TmaStage)
-template <class C, int NA, bool RED, int MINB, int STASH = 0, int TMA = 0>
+template <class C, int NA, int RED, int MINB, int STASH = 0, int TMA = 0>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
                size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
@@ -582,7 +660,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
     const Tw<W> *stab = nullptr;
     if constexpr (TMA) {
         static_assert(C::NPASS >= 3 && C::PPC == 1, "TMA staging is built for the three-pass, one-polynomial-per-CTA shapes");
-        unsigned char *buf = smem_raw + (size_t)(NA + STASH) * C::PPC * C::N * sizeof(W);
+        unsigned char *buf = smem_raw + ((size_t)NA * C::TILE + (size_t)STASH * C::PPC * C::N) * sizeof(W);
         tma_s.init(buf + kTwBufBytes, buf);
         tma = &tma_s;
         stab = reinterpret_cast<const Tw<W> *>(buf);
@@ -594,7 +672,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
         W x[1][C::R];
         // STASH = 1: second shared tile; STASH = 2: the output row itself (global memory, stays in L2), which
         // leaves the CTA with one tile of shared memory and the SM with a larger L1 for the twiddle tables
-        W *stash = (STASH == 2) ? (c + off + threadIdx.x) : (tile + C::PPC * C::N + threadIdx.x);
+        W *stash = (STASH == 2) ? (c + off + threadIdx.x) : (tile + NA * C::TILE + threadIdx.x);
 #if defined(TNTT_X_PREFETCH_B)
         // b's row is needed one forward transform from now: pull it into L2 (one 128-byte line per thread)
         if (threadIdx.x * 16 < C::N) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + off + threadIdx.x * 16));
@@ -613,8 +691,11 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
             W u;
             if constexpr (STASH) u = stash[k * C::THREADS];
             else u = fa[k];
-            if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);  // u < 2^(BITS-1): no overflow
-            fa[k] = mont_mul(u, x[0][k], mod);
+#if defined(TNTT_X_NO_POINTWISE)
+            fa[k] = u ^ x[0][k];   // what-if only
+#else
+            fa[k] = pointwise_product<C, RED>(u, x[0][k], mod);
+#endif
         }
     } else {
         W x[2][C::R];
@@ -623,9 +704,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
         forward_all<C, 2, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, true);
 #pragma unroll
         for (int k = 0; k < C::R; ++k) {
-            W u = x[0][k];
-            if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
-            fa[k] = mont_mul(u, x[1][k], mod);
+            fa[k] = pointwise_product<C, RED>(x[0][k], x[1][k], mod);
         }
     }
     dit_all<C, RED, pointwise_out_bound<C, RED>(), (TMA != 0), C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod, tma, stab);
@@ -653,7 +732,7 @@ polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restr
 // bitrev(p) = (bitrev_R(k) << log2 P) | bitrev_P(t).  For P <= 32 a warp's permuted accesses still cover whole
 // contiguous segments, so the permutation costs nothing; otherwise it goes through the tile once.  The tables
 // decide the transform: merged-psi pyramid = ntt(twist(.)), cyclic pyramid (host::fwd_pyramid_cyclic) = cg_ntt.
-template <class C, bool RED, int MINB, bool NATURAL = false>
+template <class C, int RED, int MINB, bool NATURAL = false>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
                         const __grid_constant__ PolymulTables<typename C::W> tb,
@@ -696,7 +775,7 @@ spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__r
 
 // TABLE: the store multiplies by the per-coefficient table `post` (psi^-i N^-1: twisted inverse) or, TABLE = false,
 // by the one factor `post_uniform` (N^-1: cg_intt)
-template <class C, bool RED, int MINB, bool NATURAL = false, bool TABLE = true>
+template <class C, int RED, int MINB, bool NATURAL = false, bool TABLE = true>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
                         const __grid_constant__ DitTables<typename C::W> inv, const Tw<typename C::W> *__restrict__ post,
@@ -730,7 +809,7 @@ spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__r
 }
 
 // b_stride = N: one spectrum per row; b_stride = 0: one spectrum shared by the whole batch
-template <class C, bool RED, int MINB>
+template <class C, int RED, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 polymul_spectrum_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ bspec,
                         typename C::W *__restrict__ c, size_t batch, size_t b_stride,
@@ -753,9 +832,7 @@ polymul_spectrum_kernel(const typename C::W *__restrict__ a, const typename C::W
     forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
 #pragma unroll
     for (int k = 0; k < C::R; ++k) {
-        W u = x[0][k];
-        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
-        fa[k] = mont_mul(u, __ldg(brow + (k << C::LOGP) + tid), mod);     // < u*q/2^BITS + q: below two units
+        fa[k] = pointwise_product<C, RED>(x[0][k], __ldg(brow + (k << C::LOGP) + tid), mod);   // red 1: < u*q/2^BITS + q, below two units
     }
     dit_all<C, RED, 2, false, C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod);
     row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
@@ -818,7 +895,7 @@ __device__ __forceinline__ void cluster_exchange(typename C::W (&x)[C::R], typen
 
 // PRELOAD: fetch the next pass's twiddles into registers before the cluster barrier, so that their L2 latency
 // overlaps the exchange
-template <class C, int CS, bool RED, bool PRELOAD, int XI, int PASS = 1>
+template <class C, int CS, int RED, bool PRELOAD, int XI, int PASS = 1>
 __device__ __forceinline__ void cluster_forward_rest(typename C::W (&x)[1][C::R], typename C::W *tiles, int gtid,
                                                      const PolymulTables<typename C::W> &tb, const Mod<typename C::W> &mod) {
     if constexpr (PASS < C::NPASS) {
@@ -829,7 +906,7 @@ __device__ __forceinline__ void cluster_forward_rest(typename C::W (&x)[1][C::R]
         cluster_forward_rest<C, CS, RED, PRELOAD, XI, PASS + 1>(x, tiles, gtid, tb, mod);
     }
 }
-template <class C, int CS, bool RED, bool PRELOAD, int IN_BND, int XI, int PASS = 1>
+template <class C, int CS, int RED, bool PRELOAD, int IN_BND, int XI, int PASS = 1>
 __device__ __forceinline__ void cluster_inverse_rest(typename C::W (&x)[C::R], typename C::W *tiles, int gtid,
                                                      const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod) {
     if constexpr (PASS < C::NPASS) {
@@ -842,7 +919,7 @@ __device__ __forceinline__ void cluster_inverse_rest(typename C::W (&x)[C::R], t
 }
 
 // launched with a cluster dimension of CS (cudaLaunchKernelEx); grid = rows * CS CTAs of P / CS threads
-template <class C, int CS, bool RED, int MINB = 1>
+template <class C, int CS, int RED, int MINB = 1>
 __global__ void __launch_bounds__(C::P / CS, MINB)
 polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
                        size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
@@ -875,9 +952,7 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
     cluster_forward_rest<C, CS, RED, PRELOAD, NX>(x, tiles, gtid, tb, mod);
 #pragma unroll
     for (int k = 0; k < C::R; ++k) {
-        W u = fa[k];
-        if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
-        fa[k] = mont_mul(u, x[0][k], mod);
+        fa[k] = pointwise_product<C, RED>(fa[k], x[0][k], mod);
     }
     dit_pass<C, 0, RED, pointwise_out_bound<C, RED>()>(fa, gtid, tb.inv, mod);
     cluster_inverse_rest<C, CS, RED, PRELOAD, pointwise_out_bound<C, RED>(), 2 * NX>(fa, tiles, gtid, tb.inv, mod);
@@ -891,7 +966,7 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
 //   MODE 3: polymul_spectrum   (a coefficients, b spectrum with row stride b_stride, out = c; post = tb.post)
 // The spectrum order is the same as in the one-CTA kernels: word k*P + t = bit-reversed-order element t*R + k, with t
 // the row-wide thread index (cluster rank * threads + threadIdx).
-template <class C, int CS, bool RED, int MINB, int MODE>
+template <class C, int CS, int RED, int MINB, int MODE>
 __global__ void __launch_bounds__(C::P / CS, MINB)
 spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
                         size_t batch, size_t b_stride, const __grid_constant__ PolymulTables<typename C::W> tb,
@@ -933,9 +1008,7 @@ spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W
         } else {
 #pragma unroll
             for (int k = 0; k < C::R; ++k) {
-                W u = x[0][k];
-                if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);
-                fa[k] = mont_mul(u, __ldg(brow + (k << C::LOGP) + gtid), mod);
+                fa[k] = pointwise_product<C, RED>(x[0][k], __ldg(brow + (k << C::LOGP) + gtid), mod);
             }
             dit_pass<C, 0, RED, 2>(fa, gtid, tb.inv, mod);
             cluster_inverse_rest<C, CS, RED, true, 2, NX>(fa, tiles, gtid, tb.inv, mod);
@@ -949,7 +1022,7 @@ spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W
 //   out = post * DFT_root(pre * in), all in natural order.  The bit-reversal of cg_ntt.py:39 /
 //   rtl/ntt_coeff_banks.v:112 happens on the way into the shared tile.
 // ---------------------------------------------------------------------------------------------
-template <class C, bool RED, int MINB>
+template <class C, int RED, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
                  const __grid_constant__ TransformTables<typename C::W> tb,

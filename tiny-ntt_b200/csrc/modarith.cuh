@@ -239,44 +239,55 @@ template <typename W> TNTT_HD void ct_butterfly(W &x, W &y, const Tw<W> &t, cons
 }
 
 // First stage of a decimation-in-time transform: its twiddle is 1, so no product is needed, only
-// (x, y) <- (x + y, x - y + c) with c = m.triv_c, a multiple of q that is >= y.
-template <typename W> TNTT_HD void trivial_butterfly(W &x, W &y, const Mod<W> &m) {
+// (x, y) <- (x + y, x - y + c) with c a multiple of q that is >= y (Mod::triv_c, or 2q in the Solinas kernels).
+template <typename W> TNTT_HD void trivial_butterfly(W &x, W &y, W c) {
 #if !defined(__CUDA_ARCH__) && defined(TNTT_AUDIT_RANGES)
     {
         const unsigned __int128 lim = (unsigned __int128)1 << WordTraits<W>::BITS;
-        if ((unsigned __int128)x + y >= lim || y > m.triv_c || (unsigned __int128)x + m.triv_c >= lim + y) ++g_range_violations;
+        if ((unsigned __int128)x + y >= lim || y > c || (unsigned __int128)x + c >= lim + y) ++g_range_violations;
     }
 #endif
     const W s = x + y;
-    y = x - y + m.triv_c;
+    y = x - y + c;
     x = s;
 }
 
-// Compile-time range bookkeeping, in units of 2^(BITS-4): every register entering butterfly stage number
-// `stage` (counted from the start of a transform whose inputs are below `b0` units) is below
-// bound_at(...) units.  With `red` set, a stage whose outputs could pass 16 units (= 2^BITS) first
-// applies csub_top() to its un-multiplied inputs, which brings them below 8 units (2^(BITS-1)).
-// Units are >= q because q < 2^(BITS-4) whenever `red` is used.
-TNTT_CX bool stage_needs_reduction(bool red, int g, int bound_in) { return red && bound_in + g > 16; }
-TNTT_CX int bound_after_stage(bool red, int g, int bound_in) {
-    return (stage_needs_reduction(red, g, bound_in) ? 8 : bound_in) + g;
+// Compile-time range bookkeeping.  `red` selects how lazy values are kept below 2^BITS:
+//   0: never (q is small enough for the whole transform, host::lazy_full_ok)
+//   1: csub_top() -- test the top bit, subtract floor(2^(BITS-1)/q) q.  Bounds are counted in units of 2^(BITS-4)
+//      (>= q because q < 2^(BITS-4)); a register below b units comes out below max(8, b - 7) units
+//      (top_sub > 2^(BITS-1) - q > 7 units).
+//   2: solinas_reduce() for q = 2^60 - 2^14 + 1 (64-bit words): x - (x >> 60) q < q + 2^18, a FULL reduction in three
+//      instructions.  Bounds are counted in units of q (16 q < 2^64); a reduced register is below 2 units.
+// Every register entering butterfly stage number `stage` (counted from the start of a transform whose inputs are
+// below `b0` units) is below bound_at(...) units; a stage whose outputs could pass 16 units first reduces its
+// un-multiplied inputs (the multiplied ones go through the product, which accepts any word).
+TNTT_CX int reduce_result_bound(int red, int bound_in) { return red == 2 ? 2 : (bound_in - 7 > 8 ? bound_in - 7 : 8); }
+#if defined(TNTT_X_NO_REDUCE)
+TNTT_CX bool stage_needs_reduction(int, int, int) { return false; }   // what-if only: wrong results
+#else
+TNTT_CX bool stage_needs_reduction(int red, int g, int bound_in) { return red && bound_in + g > 16; }
+#endif
+TNTT_CX int bound_after_stage(int red, int g, int bound_in) {
+    return (stage_needs_reduction(red, g, bound_in) ? reduce_result_bound(red, bound_in) : bound_in) + g;
 }
-TNTT_CX int bound_at(bool red, int g, int b0, int stage) {
+TNTT_CX int bound_at(int red, int g, int b0, int stage) {
     int b = b0;
     for (int s = 0; s < stage; ++s) b = bound_after_stage(red, g, b);
     return b;
 }
-// DIT transforms whose first stage is multiplication-free: that stage takes inputs below b0 <= 7 units to
-// outputs below b0 + 8 (x + y < 2 b0; x - y + triv_c with triv_c < 8 units).
+// DIT transforms whose first stage is multiplication-free, (x, y) <- (x + y, x - y + c) with c a multiple of q >= y:
+//   red 1: c = Mod::triv_c < 8 units serves inputs below b0 <= 7 units; outputs below b0 + 8
+//   red 2: c = 2 q serves inputs below b0 <= 2 units (of q); outputs below 2 b0
 constexpr int kTrivMaxIn = 7;
 #if defined(TNTT_NO_TRIVIAL)
-TNTT_CX bool dit_trivial_ok(bool, int) { return false; }
+TNTT_CX bool dit_trivial_ok(int, int) { return false; }
 #else
-TNTT_CX bool dit_trivial_ok(bool red, int b0) { return !red || b0 <= kTrivMaxIn; }
+TNTT_CX bool dit_trivial_ok(int red, int b0) { return !red || (red == 2 ? b0 <= 2 : b0 <= kTrivMaxIn); }
 #endif
-TNTT_CX int dit_bound_at(bool red, int g, int b0, int stage) {
+TNTT_CX int dit_bound_at(int red, int g, int b0, int stage) {
     if (!dit_trivial_ok(red, b0) || stage == 0) return bound_at(red, g, b0, stage);
-    int b = b0 + 8;
+    int b = red == 2 ? 2 * b0 : b0 + 8;
     for (int s = 1; s < stage; ++s) b = bound_after_stage(red, g, b);
     return b;
 }
@@ -292,6 +303,77 @@ TNTT_HD uint64_t mont_mul(uint64_t x, uint64_t y, const Mod<uint64_t> &m) {
     const uint64_t t = lo * m.nqinv;
     return hi + mulhi(t, m.q) + (lo != 0 ? 1u : 0u);  // lo + lo(t*q) == 0 mod 2^64, carry iff lo != 0
 }
+
+// ---------------------------------------------------------------- q = 2^60 - 2^14 + 1 (the reference's 60-bit prime)
+// 2^60 = 2^14 - 1 (mod q), so a value splits as A + B 2^60 = A + B (2^14 - 1): reductions are shifts and adds on the
+// ALU pipe instead of products on the (saturated) multiplier pipe.  Selected at plan time (tntt_plan_info.solinas)
+// for rtl/ntt_poly_mult.sv:16-26's modulus only; every other modulus keeps csub_top() / mont_mul().
+constexpr uint64_t kSolinasQ = (1ull << 60) - (1ull << 14) + 1;
+// any word x -> x - (x >> 60) q = (x mod 2^60) + (x >> 60)(2^14 - 1) < 2^60 + 15 * 2^14 < q + 2^18:
+// LOP3 + SHF + one IMAD.WIDE (the product lands on the masked word pair)
+TNTT_HD uint64_t solinas_reduce(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo, hi;
+    unpack64(x, lo, hi);
+    const uint32_t t = hi >> 28;
+    uint64_t r = pack64(lo, hi & 0x0FFFFFFFu);
+    asm("mad.wide.u32 %0, %1, 16383, %0;" : "+l"(r) : "r"(t));
+    return r;
+#else
+    return (x & ((1ull << 60) - 1)) + (x >> 60) * 16383ull;
+#endif
+}
+// u * v mod q for ANY words u, v; result < 2^60 + 2^37 (below 2 q).  Four wide multiplies for the 128-bit product,
+// then two folds: P = A + B 2^60 -> S = A + (B << 14) - B < 2^83 -> A' + B' 2^60 -> A' + (B' << 14) - B'.
+TNTT_HD uint64_t solinas_mul(uint64_t u, uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    uint32_t u0, u1, v0, v1;
+    unpack64(u, u0, u1);
+    unpack64(v, v0, v1);
+    uint64_t t0, t1, t2, t3;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t0) : "r"(u0), "r"(v0));
+    uint32_t p0, t0h;
+    unpack64(t0, p0, t0h);
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t1) : "r"(u0), "r"(v1), "l"((uint64_t)t0h));
+    uint32_t t1l, t1h;
+    unpack64(t1, t1l, t1h);
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t2) : "r"(u1), "r"(v0), "l"((uint64_t)t1l));
+    uint32_t p1, t2h;
+    unpack64(t2, p1, t2h);
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t3) : "r"(u1), "r"(v1), "l"((uint64_t)t1h));
+    uint32_t p2, p3;
+    unpack64(t3, p2, p3);
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(p2), "+r"(p3) : "r"(t2h));
+    const uint32_t a1 = p1 & 0x0FFFFFFFu, b2 = p3 >> 28;
+    uint32_t b0, b1, c1, c2;
+    asm("shf.r.wrap.b32 %0, %1, %2, 28;" : "=r"(b0) : "r"(p1), "r"(p2));
+    asm("shf.r.wrap.b32 %0, %1, %2, 28;" : "=r"(b1) : "r"(p2), "r"(p3));
+    const uint32_t c0 = b0 << 14;
+    asm("shf.l.wrap.b32 %0, %1, %2, 14;" : "=r"(c1) : "r"(b0), "r"(b1));
+    asm("shf.l.wrap.b32 %0, %1, %2, 14;" : "=r"(c2) : "r"(b1), "r"(b2));
+    uint32_t s0, s1, s2;
+    asm("add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 %1, %4, %6;\n\taddc.u32 %2, %7, 0;\n\t"
+        "sub.cc.u32 %0, %0, %8;\n\tsubc.cc.u32 %1, %1, %9;\n\tsubc.u32 %2, %2, %10;"
+        : "=&r"(s0), "=&r"(s1), "=&r"(s2) : "r"(p0), "r"(a1), "r"(c0), "r"(c1), "r"(c2), "r"(b0), "r"(b1), "r"(b2));
+    const uint32_t a1b = s1 & 0x0FFFFFFFu;
+    uint32_t bb;
+    asm("shf.r.wrap.b32 %0, %1, %2, 28;" : "=r"(bb) : "r"(s1), "r"(s2));
+    const uint32_t d0 = bb << 14, d1 = bb >> 18;
+    uint32_t r0, r1;
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;\n\tsub.cc.u32 %0, %0, %6;\n\tsubc.u32 %1, %1, 0;"
+        : "=&r"(r0), "=&r"(r1) : "r"(s0), "r"(a1b), "r"(d0), "r"(d1), "r"(bb));
+    return pack64(r0, r1);
+#else
+    const unsigned __int128 P = (unsigned __int128)u * v;
+    const uint64_t M = (1ull << 60) - 1;
+    const unsigned __int128 B = P >> 60;
+    const unsigned __int128 S = (P & M) + (B << 14) - B;
+    const uint64_t B2 = (uint64_t)(S >> 60);
+    return ((uint64_t)S & M) + (B2 << 14) - B2;
+#endif
+}
+TNTT_HD uint32_t solinas_reduce(uint32_t x) { return x; }            // 32-bit words never use the Solinas path
+TNTT_HD uint32_t solinas_mul(uint32_t u, uint32_t) { return u; }
 
 // The reference's Barrett product for canonical operands (rtl/barrett_reduction.v:23-29):
 //   p = a*b; q1 = p >> (k-1); q2 = (q1*mu) >> (k+1); r = p - q2*q; if (r >= q) r -= q

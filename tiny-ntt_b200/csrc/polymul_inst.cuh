@@ -4,9 +4,9 @@
 
 namespace tntt {
 
-template <class C, int NA, bool RED, int MINB, int STASH = 0, int TMA = 0> struct PolymulInst {
+template <class C, int NA, int RED, int MINB, int STASH = 0, int TMA = 0> struct PolymulInst {
     using W = typename C::W;
-    static constexpr size_t SMEM = (size_t)(NA + STASH) * C::PPC * C::N * sizeof(W) + (TMA ? kTwBufBytes + 16 : 0);
+    static constexpr size_t SMEM = ((size_t)NA * C::TILE + (size_t)STASH * C::PPC * C::N) * sizeof(W) + (TMA ? kTwBufBytes + 16 : 0);
     static cudaError_t launch(const void *a, const void *b, void *c, size_t batch, const void *tables, const void *mod,
                               cudaStream_t stream) {
         if (batch == 0) return cudaSuccess;
@@ -29,7 +29,7 @@ template <class C, int NA, bool RED, int MINB, int STASH = 0, int TMA = 0> struc
 };
 
 // one row per cluster of CS CTAs (small batches); launched with a cluster-dimension attribute
-template <class C, int CS, bool RED, int MINB = 1> struct PolymulClusterInst {
+template <class C, int CS, int RED, int MINB = 1> struct PolymulClusterInst {
     using W = typename C::W;
     static constexpr size_t SMEM = 2 * (size_t)(C::N / CS) * sizeof(W);
     static cudaError_t launch(const void *a, const void *b, void *c, size_t batch, const void *tables, const void *mod,
@@ -77,21 +77,29 @@ template <class C, int CS, bool RED, int MINB = 1> struct PolymulClusterInst {
 #define TNTT_POLYMUL_CLUSTER_B(WT, WB, LN, LR, CS, RED, MINB)                                                         \
     PolymulVariant {                                                                                                  \
         "u" #WB "_n" #LN "_r" #LR "_p1_a1_red" #RED "_b" #MINB "_c" #CS, WB / 8, LN, LR, 1, 1, RED,                    \
-            Cfg<WT, LN, LR, 1>::P / CS, MINB, PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::SMEM,       \
-            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::launch,                                     \
-            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::prepare,                                    \
-            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::attributes, CS                              \
+            Cfg<WT, LN, LR, 1>::P / CS, MINB, PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::SMEM,              \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::launch,                                            \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::prepare,                                           \
+            &PolymulClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::attributes, CS                                     \
     }
 
+// RED: 0 = no intermediate reduction, 1 = lazy top-bit reduction (any q < 2^60), 2 = Solinas forms for q = 2^60 - 2^14 + 1
+// PAD: 1 = padded tile instead of the XOR swizzle (64-bit words, 16 coefficients per thread)
 #define TNTT_POLYMUL_VARIANT(WT, WB, LN, LR, PPC, NA, RED, MINB) TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, 0, 0)
 #define TNTT_POLYMUL_VARIANT_S(WT, WB, LN, LR, PPC, NA, RED, MINB, ST) TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, ST, 0)
 #define TNTT_POLYMUL_VARIANT_T(WT, WB, LN, LR, PPC, NA, RED, MINB, ST, TM)                                              \
-    PolymulVariant {                                                                                          \
-        "u" #WB "_n" #LN "_r" #LR "_p" #PPC "_a" #NA "_red" #RED "_b" #MINB "_s" #ST "_t" #TM, WB / 8, LN, LR, PPC, NA, RED,     \
-            Cfg<WT, LN, LR, PPC>::THREADS, MINB, PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::SMEM, \
-            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::launch,                                 \
-            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::prepare,                                \
-            &PolymulInst<Cfg<WT, LN, LR, PPC>, NA, (RED != 0), MINB, ST, TM>::attributes                              \
+    TNTT_POLYMUL_VARIANT_X("u" #WB "_n" #LN "_r" #LR "_p" #PPC "_a" #NA "_red" #RED "_b" #MINB "_s" #ST "_t" #TM, WT, WB, LN, LR, PPC, \
+                           NA, RED, MINB, ST, TM, 0)
+#define TNTT_POLYMUL_VARIANT_P(WT, WB, LN, LR, PPC, NA, RED, MINB, ST)                                                  \
+    TNTT_POLYMUL_VARIANT_X("u" #WB "_n" #LN "_r" #LR "_p" #PPC "_a" #NA "_red" #RED "_b" #MINB "_s" #ST "_t0_pad", WT, WB, LN, LR, PPC, \
+                           NA, RED, MINB, ST, 0, 1)
+#define TNTT_POLYMUL_VARIANT_X(NAME, WT, WB, LN, LR, PPC, NA, RED, MINB, ST, TM, PAD)                                   \
+    PolymulVariant {                                                                                                  \
+        NAME, WB / 8, LN, LR, PPC, NA, RED, Cfg<WT, LN, LR, PPC, PAD>::THREADS, MINB,                                   \
+            PolymulInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST, TM>::SMEM,                                        \
+            &PolymulInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST, TM>::launch,                                     \
+            &PolymulInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST, TM>::prepare,                                    \
+            &PolymulInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST, TM>::attributes                                  \
     }
 
 }  // namespace tntt

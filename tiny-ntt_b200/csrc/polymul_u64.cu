@@ -20,6 +20,12 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 1, 1, 2, 0, 1),
     TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 1, 1, 1, 1, 1),
     TNTT_POLYMUL_VARIANT_T(uint64_t, 64, 12, 4, 1, 2, 1, 1, 0, 1),
+    // round 2: two operands side by side over padded tiles (immediate-offset exchanges), deeper twiddle groups; red2 = the
+    // Solinas reductions, matched only by q = 2^60 - 2^14 + 1 (profiles/r02_whatif_*.log)
+    TNTT_POLYMUL_VARIANT_P(uint64_t, 64, 12, 4, 1, 2, 1, 2, 0),
+    TNTT_POLYMUL_VARIANT_P(uint64_t, 64, 12, 4, 1, 2, 2, 2, 0),
+    TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 12, 4, 1, 1, 2, 3, 1),
+    TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 4, 1, 2, 2, 2),
     // small batches: one row per cluster of 4 CTAs, exchanges through distributed shared memory
     TNTT_POLYMUL_CLUSTER(uint64_t, 64, 12, 3, 4, 1),
     TNTT_POLYMUL_CLUSTER(uint64_t, 64, 12, 3, 4, 0),

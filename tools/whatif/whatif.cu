@@ -47,7 +47,13 @@ using W = uint64_t;
 constexpr uint64_t Q = 1152921504606830593ull, PSI = 431606828070683274ull;
 constexpr bool kRed = true;
 #endif
-using C = Cfg<W, 12, W_LOGR, 1>;
+#ifndef W_PAD
+#define W_PAD 0
+#endif
+#ifndef W_RED
+#define W_RED (kRed ? 1 : 0)     // 2 = Solinas reductions (q = 2^60 - 2^14 + 1 only)
+#endif
+using C = Cfg<W, 12, W_LOGR, 1, W_PAD>;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -67,7 +73,7 @@ int main(int argc, char **argv) {
     PolymulTables<W> tb;
     tb.fwd_pyr = upload(fwd);
     tb.fwd_last = upload(host::fwd_last_table<W>(fwd, 12, W_LOGR));
-    tb.post = upload(host::scaled_powers<W>(psi_inv, host::mulmod(n_inv, r_mod_q, Q), n, Q));
+    tb.post = upload(host::scaled_powers<W>(psi_inv, W_RED == 2 ? n_inv : host::mulmod(n_inv, r_mod_q, Q), n, Q));   // Solinas pointwise: no 2^-64
     tb.inv.pyr = upload(inv);
     for (int i = 0; i < MAX_R; ++i) { tb.fwd_head[i] = fwd[i]; tb.inv.head[i] = inv[i]; }
 
@@ -79,8 +85,8 @@ int main(int argc, char **argv) {
     W *da = upload(a), *db = upload(b), *dc;
     CK(cudaMalloc(&dc, rows * n * sizeof(W)));
 
-#ifdef W_CLUSTER
-    auto kern = polymul_cluster_kernel<C, W_CLUSTER, kRed>;
+#if defined(W_CLUSTER)
+    auto kern = polymul_cluster_kernel<C, W_CLUSTER, W_RED>;
     const size_t smem = 2 * (C::N / W_CLUSTER) * sizeof(W);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kern));
@@ -94,8 +100,8 @@ int main(int argc, char **argv) {
         CK(cudaLaunchKernelEx(&cfg, kern, (const W *)da, (const W *)db, dc, rows, tb, mod));
     };
 #else
-    auto kern = polymul_kernel<C, W_NA, kRed, W_MINB, W_STASH, W_TMA>;
-    const size_t smem = (size_t)(W_NA + (W_STASH == 1 ? 1 : 0)) * C::N * sizeof(W) + (W_TMA ? kTwBufBytes + 16 : 0);
+    auto kern = polymul_kernel<C, W_NA, W_RED, W_MINB, W_STASH, W_TMA>;
+    const size_t smem = ((size_t)W_NA * C::TILE + (W_STASH == 1 ? C::N : 0)) * sizeof(W) + (W_TMA ? kTwBufBytes + 16 : 0);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kern));
     int bps = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, C::THREADS, smem));
