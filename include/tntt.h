@@ -15,7 +15,10 @@
  *  - Calls enqueue work on `cuda_stream` (a cudaStream_t; NULL = default stream) and return without
  *    synchronising.  The library never allocates per call on the fused paths (tables live in the
  *    plan) and never frees caller memory.
- *  - A plan is immutable after creation and may be used from several host threads / streams.
+ *  - A plan's tables are immutable after creation and the device entry points may be called on it from
+ *    several host threads / streams.  Two things are NOT thread-safe: tntt_plan_set_default_variant (a
+ *    benchmarking knob that rewrites the plan's dispatch fields; call it before sharing the plan) and
+ *    tntt_polymul_host, which serialises callers on the plan's one set of staging buffers.
  *    One plan per device.  There is NO CPU fallback: without a CUDA device tntt_plan_create fails
  *    with TNTT_NO_DEVICE.
  *  - Return value: 0 = TNTT_OK, negative = error; tntt_last_error() gives a thread-local message.
@@ -30,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TNTT_VERSION 101 /* 0.1.1 */
+#define TNTT_VERSION 200 /* 0.2.0 */
 
 enum tntt_status {
     TNTT_OK = 0,
@@ -113,10 +116,16 @@ int tntt_pointwise(const tntt_plan *plan, const void *a, const void *b, void *c,
  * one HBM round trip per polynomial. */
 int tntt_polymul(const tntt_plan *plan, const void *a, const void *b, void *c, size_t batch, void *cuda_stream);
 
-/* Same through HOST buffers (pinned for full overlap): 32 MiB chunks, H2D -> kernel -> D2H over three
- * streams.  The GPU analogue of the RoCC load/start/read command sequence
- * (chipyard/ntt-test.c:110-169).  Blocks until c is complete. */
+/* Same through HOST buffers (pinned for full overlap): chunks ramping up to 64 MiB per operand
+ * (TNTT_HOST_CHUNK_MB overrides), H2D -> kernel -> D2H rotating over four streams / buffer sets.  The GPU
+ * analogue of the RoCC load/start/read command sequence (chipyard/ntt-test.c:110-169).  Blocks until c is
+ * complete; on an error every queued copy is drained before the call returns. */
 int tntt_polymul_host(tntt_plan *plan, const void *a_host, const void *b_host, void *c_host, size_t batch);
+/* The same over several GPUs from ONE process (per-device plan + streams, batch split
+ * into contiguous ranges of ceil(batch / nplans) rows, host barrier): plans[i] must be plans of the same ring on
+ * distinct devices.  One host thread per device runs that device's pipeline; returns when all of c is complete. */
+int tntt_polymul_host_multi(tntt_plan *const *plans, int nplans, const void *a_host, const void *b_host, void *c_host,
+                            size_t batch);
 
 /* Literal constant-geometry schedule, one stage per call (cg_ntt.py:49-59,
  * rtl/ntt_cg_address_gen.v:57-117): out[i] = in[2i] + w*in[2i+1], out[i+n/2] = in[2i] - w*in[2i+1],
@@ -159,6 +168,30 @@ int tntt_variant_matches(const tntt_plan *plan, int variant);        /* 1 if usa
 int tntt_polymul_variant(const tntt_plan *plan, int variant, const void *a, const void *b, void *c, size_t batch,
                          void *cuda_stream);
 int tntt_plan_set_default_variant(tntt_plan *plan, int variant);
+
+/* ---- multi-modulus (RNS) batches: SURVEY.md section 8 f3; reports/final-report.tex:1811-1817 ----
+ * An RNS polynomial batch is [limbs][batch][n] words: limb l holds the residues mod q[l].  All limbs must need
+ * the same word size (see tntt_plan_info.word_bytes).  The tables of every limb (the contents of
+ * scripts/generate_twiddles.py:29-41 / generate_inverse_twiddles.py:48-61 in kernel order, with their Shoup
+ * companions) are generated on the device by one kernel launch from (q[l], psi[l]). */
+typedef struct tntt_rns_plan tntt_rns_plan;
+int tntt_rns_plan_create(tntt_rns_plan **out, int device, uint32_t n, const uint64_t *q, const uint64_t *psi, int limbs);
+void tntt_rns_plan_destroy(tntt_rns_plan *plan);
+int tntt_rns_plan_limbs(const tntt_rns_plan *plan);
+int tntt_rns_plan_word_bytes(const tntt_rns_plan *plan);
+const char *tntt_rns_plan_kernel(const tntt_rns_plan *plan);       /* name of the kernel shape in use */
+size_t tntt_rns_plan_table_bytes(const tntt_rns_plan *plan);       /* device memory held by the tables */
+/* c[l] = a[l] * b[l] in Z_{q_l}[x]/(x^n+1) for every limb: ONE kernel launch per 16 limbs (the limb index is
+ * blockIdx.y; tables and modulus constants are picked out of the kernel parameters). */
+int tntt_rns_polymul(const tntt_rns_plan *plan, const void *a, const void *b, void *c, size_t batch, void *cuda_stream);
+/* test hook: regenerates limb `limb`'s tables with the host generators and compares them word for word with the
+ * device-generated ones (TNTT_OK = identical) */
+int tntt_rns_plan_check_tables(const tntt_rns_plan *plan, int limb);
+int tntt_rns_kernel_attributes(const tntt_rns_plan *plan, int *regs, size_t *local_bytes, int *ctas_per_sm);
+/* scripts/find_psi.py:9-44: the smallest psi in [2, max_search) with psi^n = -1 mod q (the script's own
+ * max_search is 10000) -> returns 0.  If there is none that small the script gives up; this continues with
+ * g^((q-1)/2n), g = 2, 3, ... and returns 1.  Host-side, like the script. */
+int tntt_find_psi(uint32_t n, uint64_t q, uint64_t max_search, uint64_t *psi);
 
 /* Integer-pipe microbenchmark (measurement only): kind 0 = IMAD.LO, 1 = IMAD.WIDE.U32, 2 = IADD3,
  * 3 = exact 64-bit Shoup modmul chain, 4 = 32-bit Shoup modmul chain, 5 = the 64-bit butterfly product

@@ -26,6 +26,7 @@ def lib():
         L.emu_slot.argtypes = [C.c_int] * 7
         L.emu_polymul_ex.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3 + [C.c_size_t, C.c_uint64, C.c_uint64]
         L.emu_slot_ex.argtypes = [C.c_int] * 8
+        L.emu_cluster_exchange_violations.argtypes = [C.c_int] * 5
         L.emu_solinas_reduce.argtypes = [C.c_uint64]
         L.emu_solinas_reduce.restype = C.c_uint64
         L.emu_solinas_mul.argtypes = [C.c_uint64] * 2

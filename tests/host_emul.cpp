@@ -208,14 +208,14 @@ template <class C, int NA, int RED>
 int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q, uint64_t psi) {
     using W = typename C::W;
     constexpr int BITS = WordTraits<W>::BITS;
-    if (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN)) return -2;
+    if (RED == 3 ? q >= (1ull << 60) : (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN))) return -2;
     if (RED == 2 && q != kSolinasQ) return -2;
     const uint64_t omega = host::mulmod(psi, psi, q);
     auto fwd = host::fwd_pyramid<W>(psi, C::N, q);
     auto last = host::fwd_last_table<W>(fwd, C::LOGN, C::LOGR);
     auto inv = host::dit_pyramid<W>(host::modinv(omega, q), C::N, q);
     // the Montgomery pointwise product (red 0/1) leaves a factor 2^-BITS for the store table to undo; the Solinas one does not
-    const uint64_t scale = RED == 2 ? host::modinv(C::N % q, q)
+    const uint64_t scale = RED >= 2 ? host::modinv(C::N % q, q)
                                     : host::mulmod(host::modinv(C::N % q, q), (uint64_t)((((host::u128)1) << BITS) % q), q);
     auto post = host::scaled_powers<W>(host::modinv(psi, q), scale, C::N, q);
     Emu<C, NA, RED> e;
@@ -235,7 +235,7 @@ template <class C, bool RED>
 int run_spectrum(const void *a, const void *b, void *out, size_t batch, uint64_t q, uint64_t psi, int mode) {
     using W = typename C::W;
     constexpr int BITS = WordTraits<W>::BITS;
-    if (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN)) return -2;
+    if (RED == 3 ? q >= (1ull << 60) : (RED ? !host::lazy_pass_ok<W>(q, C::LOGR) : !host::lazy_full_ok<W>(q, C::LOGN))) return -2;
     const uint64_t omega = host::mulmod(psi, psi, q), n_inv = host::modinv(C::N % q, q);
     auto fwd = host::fwd_pyramid<W>(psi, C::N, q);
     auto last = host::fwd_last_table<W>(fwd, C::LOGN, C::LOGR);
@@ -339,6 +339,9 @@ int emu_spectrum(int word_bytes, int logn, int logr, int ppc, int red, const voi
 // red: 0 / 1 / 2 (Solinas, q = 2^60 - 2^14 + 1 only); pad: 1 = padded tile
 int emu_polymul_ex(int word_bytes, int logn, int logr, int ppc, int na, int red, int pad, const void *a, const void *b, void *c,
                    size_t batch, uint64_t q, uint64_t psi) {
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 1, 3, 0)
+    POLY_CASE_P(8, uint64_t, 12, 4, 1, 2, 3, 1)
+    POLY_CASE_P(8, uint64_t, 8, 4, 16, 1, 3, 0)
     POLY_CASE_P(8, uint64_t, 12, 4, 1, 1, 1, 1)
     POLY_CASE_P(8, uint64_t, 12, 4, 1, 2, 1, 1)
     POLY_CASE_P(8, uint64_t, 12, 4, 1, 1, 2, 0)
@@ -402,6 +405,32 @@ int emu_transform(int word_bytes, int logn, int logr, int ppc, int red, const vo
     XFORM_CASE(8, uint64_t, 12, 4, 1, 1)
     XFORM_CASE(8, uint64_t, 12, 3, 1, 1)
     return -1;
+}
+
+// Distributed-shared-memory addressing of cluster_exchange() (kernels.cuh), replayed for every thread of a row: each
+// (destination CTA, slot) must lie inside the cluster and its N / CS-word buffer, be written exactly once, and hold the
+// coefficient its reader -- thread g2 of the row, register k2, slot k2 * T + g2 % T of CTA g2 / T -- owns in the next
+// layout.  Returns the number of violations.
+int emu_cluster_exchange_violations(int logn, int logr, int cs, int lo_from, int lo_to) {
+    const int N = 1 << logn, R = 1 << logr, P = N / R, T = P / cs;
+    if (T * cs != P) return -1;
+    auto elem = [&](int lo, int tid, int k) { return ((tid >> lo) << (lo + logr)) | (k << lo) | (tid & ((1 << lo) - 1)); };
+    std::vector<int> buf((size_t)cs * (N / cs), -1);
+    int bad = 0;
+    for (int gtid = 0; gtid < P; ++gtid)
+        for (int k = 0; k < R; ++k) {
+            const int E = elem(lo_from, gtid, k);
+            const int g2 = ((E >> (lo_to + logr)) << lo_to) | (E & ((1 << lo_to) - 1));
+            const int k2 = (E >> lo_to) & (R - 1);
+            const int cta = g2 / T, slot = k2 * T + (g2 % T);
+            if (cta < 0 || cta >= cs || slot < 0 || slot >= N / cs) { ++bad; continue; }
+            if (buf[(size_t)cta * (N / cs) + slot] != -1) ++bad;          // two writers
+            buf[(size_t)cta * (N / cs) + slot] = E;
+        }
+    for (int gtid = 0; gtid < P; ++gtid)                                   // the read side: buf[k * T + gtid % T] of the own CTA
+        for (int k = 0; k < R; ++k)
+            if (buf[(size_t)(gtid / T) * (N / cs) + k * T + (gtid % T)] != elem(lo_to, gtid, k)) ++bad;
+    return bad;
 }
 
 // shared-memory slot of (poly-in-cta, register k, thread tid) for a register field at bit `lo`

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/tntt.h but not exported"
     assert sorted(tntt.SYMBOLS) == declared, "python binding and header disagree"
-    assert tntt.lib().tntt_version() == 101
+    assert tntt.lib().tntt_version() == 200
     # nothing but the C ABI leaks out of the shared object
     out = subprocess.check_output(["nm", "-D", "--defined-only", tntt.LIB_PATH], text=True)
     exported = sorted(line.split()[-1] for line in out.splitlines() if " T " in line)
@@ -172,3 +172,31 @@ def test_benchmark_fixture_helpers_reproduce_the_reference_inputs_and_checksums(
         assert fixtures.make_poly(2, n, q) == case["b"], tag
         assert fixtures.checksum(case["c"], q) == fixtures.REFERENCE_CHECKSUMS[(n, q)], tag
         assert fixtures.REFERENCE_CHECKSUMS[(n, q)] in [int(v) for v in g["cpp_checksums"].values()], tag
+
+
+def test_find_psi_matches_the_reference_script():
+    """tntt_find_psi (host side) against answers of scripts/find_psi.py:9-44 run in the build container
+    (tests/golden/make_find_psi_golden.py)."""
+    import ctypes as C
+    import json
+
+    import tntt
+
+    with open(os.path.join(ROOT, "tests", "golden", "golden_find_psi.json")) as fh:
+        cases = json.load(fh)["cases"]
+    L = tntt.lib()
+    assert len(cases) >= 7
+    for c in cases:
+        psi = C.c_uint64()
+        rc = L.tntt_find_psi(c["n"], c["q"], 10000, C.byref(psi))
+        if c["psi"] is None:        # the script gives up; the library goes on and says so (rc = 1)
+            assert rc == 1
+            assert pow(psi.value, c["n"], c["q"]) == c["q"] - 1
+        else:
+            assert rc == 0 and psi.value == c["psi"], c
+        assert tntt.find_psi(c["n"], c["q"]) == psi.value
+    psi = C.c_uint64()
+    assert L.tntt_find_psi(256, 7683, 10000, C.byref(psi)) < 0          # 7683 = 3 * 13 * 197
+    assert L.tntt_find_psi(256, 7687, 10000, C.byref(psi)) < 0          # prime, but not 1 mod 512
+    with pytest.raises(ValueError):
+        tntt.find_psi(4096, 12289)

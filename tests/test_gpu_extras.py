@@ -360,3 +360,91 @@ def test_plain_c_client_of_the_transform_domain_entry_points(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "PASS" in out.stdout
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-modulus engine (csrc/rns.cu): one launch for [L, B, N], tables generated on the device
+# ------------------------------------------------------------------------------------------------
+def friendly_primes(n, count, below):
+    """`count` primes q = 1 mod 2n, descending from `below` (deterministic Miller-Rabin)."""
+    def is_prime(m):
+        if m < 2:
+            return False
+        for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            if m % p == 0:
+                return m == p
+        d, r = m - 1, 0
+        while d % 2 == 0:
+            d, r = d // 2, r + 1
+        for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            x = pow(a, d, m)
+            if x in (1, m - 1):
+                continue
+            for _ in range(r - 1):
+                x = x * x % m
+                if x == m - 1:
+                    break
+            else:
+                return False
+        return True
+
+    out, q = [], below - (below - 1) % (2 * n)
+    while len(out) < count:
+        if q < below and is_prime(q):
+            out.append(q)
+        q -= 2 * n
+    return out
+
+
+@pytest.mark.parametrize("n,limbs,below", [(4096, 1, 1 << 60), (4096, 4, 1 << 60), (4096, 16, 1 << 60), (4096, 20, 1 << 59),
+                                           (4096, 3, 1 << 50), (1024, 5, 1 << 60), (256, 4, 1 << 55),
+                                           (4096, 6, 1 << 23), (1024, 18, 1 << 23), (256, 3, 1 << 23)])
+def test_rns_one_launch_matches_oracle_limb_by_limb(n, limbs, below):
+    import tntt
+
+    co = COracle()
+    moduli = friendly_primes(n, limbs, below)
+    psis = [tntt.find_psi(n, q) for q in moduli]
+    ctx = tntt.RnsContext(n, moduli, psis)
+    assert ctx.word_bytes == (4 if below <= (1 << 23) else 8)
+    for l in {0, limbs // 2, limbs - 1}:
+        assert ctx.tables_match_host_generators(l), tntt.lib().tntt_last_error()
+    rng = np.random.default_rng(n + limbs)
+    npdt, sdt = (np.uint32, np.int32) if ctx.word_bytes == 4 else (np.uint64, np.int64)
+    for rows in (1, 7, 33):
+        a = np.stack([rng.integers(0, q, size=(rows, n), dtype=np.uint64) for q in moduli])
+        b = np.stack([rng.integers(0, q, size=(rows, n), dtype=np.uint64) for q in moduli])
+        for l, q in enumerate(moduli):
+            a[l, 0], b[l, 0] = q - 1, q - 1                  # largest canonical values
+        da = torch.from_numpy(a.astype(npdt).view(sdt)).cuda()
+        db = torch.from_numpy(b.astype(npdt).view(sdt)).cuda()
+        got = ctx.polymul(da, db).cpu().numpy().view(npdt).astype(np.uint64)
+        for l, (q, psi) in enumerate(zip(moduli, psis)):
+            assert (got[l] == co.nwc_poly_mult(a[l], b[l], psi, q, threads=8)).all(), (l, q)
+    # the single-modulus plans (host-built tables) give the same bits
+    single = torch.stack([tntt.polymul(pl, da[l], db[l]) for l, pl in enumerate(ctx.plans)])
+    assert torch.equal(single, ctx.polymul(da, db))
+
+
+def test_rns_context_rejects_what_it_cannot_run():
+    import tntt
+
+    q60 = friendly_primes(4096, 2, 1 << 60)
+    q23 = friendly_primes(4096, 1, 1 << 23)
+    with pytest.raises(ValueError, match="word"):
+        tntt.RnsContext(4096, q60 + q23)                       # mixed word sizes
+    with pytest.raises(ValueError, match="repeats"):
+        tntt.RnsContext(4096, [q60[0], q60[0]])
+    with pytest.raises(ValueError, match="psi"):
+        tntt.RnsContext(4096, q60, [3, 5])
+    with pytest.raises(ValueError):
+        tntt.RnsContext(4096, [q60[0] + 2])                    # not prime / not 1 mod 2n
+    ctx = tntt.RnsContext(4096, q60)
+    a = torch.zeros((2, 3, 4096), dtype=torch.int64, device="cuda")
+    with pytest.raises(ValueError):
+        ctx.polymul(a[:1], a[:1])
+    with pytest.raises(TypeError):
+        ctx.polymul(a.to(torch.int32), a.to(torch.int32))
+    with pytest.raises(ValueError):
+        ctx.polymul(a.cpu(), a.cpu())
+    assert ctx.polymul(a[:, :0], a[:, :0]).shape == (2, 0, 4096)

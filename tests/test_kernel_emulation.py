@@ -301,3 +301,16 @@ def test_solinas_arithmetic_primitives():
         for v in edge:
             r = L.emu_solinas_mul(u, v)
             assert r % q == u * v % q and r < (1 << 60) + (1 << 37)
+
+
+@pytest.mark.parametrize("logn,logr,ppc,na,pad,tag", [(12, 4, 1, 1, 0, "n4096_60"), (12, 4, 1, 2, 1, "n4096_60"), (8, 4, 16, 1, 0, "dilithium")])
+def test_emulated_barrett_shapes(logn, logr, ppc, na, pad, tag, co):
+    """red 3: the reference's arithmetic (rtl/barrett_reduction.v:23-29 products, fully reducing adds) inside the fused kernel"""
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    rng = np.random.default_rng(logn + na)
+    a = rng.integers(0, q, size=(ppc + 2, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(ppc + 2, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    assert (emu.polymul(8, logn, logr, ppc, na, 3, a, b, q, psi, pad=pad).astype(np.uint64) == want).all()

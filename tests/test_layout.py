@@ -90,3 +90,18 @@ def test_warp_local_exchanges_stay_inside_their_thread_group(wb, logn, logr, ppc
                         g = (pl * p + t) // group
                         assert owner.setdefault(s, g) == g, (lo, layout, pl, t, k)
         assert group <= 32 and 32 % group == 0
+
+
+@pytest.mark.parametrize("logn,logr,cs", [(12, 3, 4), (14, 4, 4), (15, 4, 8), (12, 4, 2)])
+def test_cluster_exchange_addressing(logn, logr, cs):
+    """The distributed-shared-memory exchange of the cluster kernels (kernels.cuh cluster_exchange): every remote
+    store stays inside the cluster and the destination buffer, no slot has two writers, and every reader finds the
+    coefficient of its next layout -- for every regrouping a forward and an inverse transform perform."""
+    L = emu.lib()
+    npass = (logn + logr - 1) // logr
+    fwd = [max(logn - (p + 1) * logr, 0) for p in range(npass)]
+    inv = [min(p * logr, logn - logr) for p in range(npass)]
+    for los in (fwd, inv):
+        for lo_from, lo_to in zip(los, los[1:]):
+            assert L.emu_cluster_exchange_violations(logn, logr, cs, lo_from, lo_to) == 0, (lo_from, lo_to)
+    assert L.emu_cluster_exchange_violations(logn, logr, cs, fwd[0], fwd[0]) == 0      # identity regrouping

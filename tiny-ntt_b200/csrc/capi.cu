@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tntt.h"
@@ -30,6 +31,18 @@ int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+}  // namespace
+// the same, for the other translation units of the library (rns.cu, multi.cu)
+int tntt::api_fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+namespace {
 #define CUDA_TRY(expr)                                                                           \
     do {                                                                                         \
         cudaError_t e_ = (expr);                                                                 \
@@ -389,7 +402,7 @@ template <typename W> int launch_variant(const tntt_plan *p, const PolymulVarian
     tb.fwd_pyr = (const Tw<W> *)p->fwd_pyr;
     tb.fwd_last = (const Tw<W> *)p->fwd_last[v.logr];
     // the Montgomery pointwise product of red 0/1 leaves a factor 2^-BITS for the store table to undo; the Solinas one does not
-    tb.post = (const Tw<W> *)(v.red == 2 ? p->post_untwist : p->post_mont);
+    tb.post = (const Tw<W> *)(v.red >= 2 ? p->post_untwist : p->post_mont);
     tb.inv.pyr = (const Tw<W> *)p->inv_pyr;
     if constexpr (sizeof(W) == 4) { memcpy(tb.fwd_head, p->head32[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head32[1], sizeof tb.inv.head); }
     else { memcpy(tb.fwd_head, p->head64[0], sizeof tb.fwd_head); memcpy(tb.inv.head, p->head64[1], sizeof tb.inv.head); }
@@ -574,6 +587,8 @@ int tntt_variant_matches(const tntt_plan *p, int variant) {
     const PolymulVariant &v = all_variants()[variant];
     if (!p->info.has_psi || v.word_bytes != p->info.word_bytes || v.logn != (int)p->info.logn) return 0;
     // red 2 = the Solinas-form reductions: an alternative to red 1 for the one modulus they are written for
+    // red 3 = Barrett products of canonical values: serves every modulus of the 64-bit paths
+    if (v.red == 3) return v.word_bytes == 8 ? 1 : 0;
     if (v.red == 2 ? !(p->info.lazy_reduce && p->info.solinas) : v.red != p->info.lazy_reduce) return 0;
     if (v.red && !host::lazy_pass_ok<uint64_t>(p->info.q, v.logr)) return 0;
     return 1;
@@ -661,19 +676,66 @@ int tntt_polymul_host(tntt_plan *p, const void *a, const void *b, void *c, size_
     }
     const char *pa = (const char *)a, *pb = (const char *)b;
     char *pc = (char *)c;
-    int slot = 0;
+    int slot = 0, rc = TNTT_OK;
     size_t r0 = 0;
+    cudaError_t e = cudaSuccess;
+    const char *what = "";
     for (const size_t nr : head) {
         cudaStream_t st = p->pipe_stream[slot];
-        CUDA_TRY(cudaMemcpyAsync(p->pipe_buf[slot][0], pa + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(p->pipe_buf[slot][1], pb + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st));
-        int rc = tntt_polymul(p, p->pipe_buf[slot][0], p->pipe_buf[slot][1], p->pipe_buf[slot][2], nr, st);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(pc + r0 * row_bytes, p->pipe_buf[slot][2], nr * row_bytes, cudaMemcpyDeviceToHost, st));
+        what = "cudaMemcpyAsync (host to device)";
+        if ((e = cudaMemcpyAsync(p->pipe_buf[slot][0], pa + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(p->pipe_buf[slot][1], pb + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((rc = tntt_polymul(p, p->pipe_buf[slot][0], p->pipe_buf[slot][1], p->pipe_buf[slot][2], nr, st)) != TNTT_OK) break;
+        what = "cudaMemcpyAsync (device to host)";
+        if ((e = cudaMemcpyAsync(pc + r0 * row_bytes, p->pipe_buf[slot][2], nr * row_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
         r0 += nr;
         slot = (slot + 1) % tntt_plan::kSlots;
     }
-    for (int s = 0; s < tntt_plan::kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(p->pipe_stream[s]));
+    // drain every stream even after a failure: copies already queued still read a/b and write c, and the caller
+    // is free to release those buffers as soon as this returns
+    for (int s = 0; s < tntt_plan::kSlots; ++s) {
+        const cudaError_t se = cudaStreamSynchronize(p->pipe_stream[s]);
+        if (se != cudaSuccess && e == cudaSuccess && rc == TNTT_OK) { e = se; what = "cudaStreamSynchronize"; }
+    }
+    if (rc != TNTT_OK) return rc;
+    if (e != cudaSuccess) return fail(TNTT_CUDA_ERROR, "%s: %s", what, cudaGetErrorString(e));
+    return TNTT_OK;
+}
+
+// Single-process multi-GPU form of the same call: plans[i] lives on its own device
+// and takes the i-th contiguous range of ceil(batch / nplans) rows; one host thread per device drives that device's
+// pipeline; the join is the host barrier.  No data-path collective: rows are independent (cg_ntt.py:78-92).
+int tntt_polymul_host_multi(tntt_plan *const *plans, int nplans, const void *a, const void *b, void *c, size_t batch) {
+    if (!plans || nplans < 1) return fail(TNTT_BAD_ARG, "need at least one plan");
+    for (int i = 0; i < nplans; ++i) {
+        if (!plans[i]) return fail(TNTT_BAD_ARG, "plan %d is null", i);
+        if (plans[i]->info.n != plans[0]->info.n || plans[i]->info.q != plans[0]->info.q || plans[i]->info.psi != plans[0]->info.psi)
+            return fail(TNTT_BAD_ARG, "plan %d is for another ring than plan 0", i);
+        for (int j = 0; j < i; ++j)
+            if (plans[j] == plans[i] || plans[j]->info.device == plans[i]->info.device)
+                return fail(TNTT_BAD_ARG, "plans %d and %d share device %d: one plan per device", j, i, plans[i]->info.device);
+    }
+    if (batch == 0) return TNTT_OK;
+    if (!a || !b || !c) return fail(TNTT_BAD_ARG, "null argument");
+    if (nplans == 1) return tntt_polymul_host(plans[0], a, b, c, batch);
+    const size_t per = (batch + (size_t)nplans - 1) / (size_t)nplans;
+    const size_t row_bytes = (size_t)plans[0]->info.n * plans[0]->info.word_bytes;
+    std::vector<int> rcs(nplans, TNTT_OK);
+    std::vector<std::string> msgs(nplans);
+    std::vector<std::thread> workers;
+    for (int i = 0; i < nplans; ++i) {
+        const size_t r0 = per * (size_t)i < batch ? per * (size_t)i : batch;
+        const size_t rows = batch - r0 < per ? batch - r0 : per;
+        if (!rows) continue;
+        workers.emplace_back([=, &rcs, &msgs] {
+            rcs[i] = tntt_polymul_host(plans[i], (const char *)a + r0 * row_bytes, (const char *)b + r0 * row_bytes,
+                                       (char *)c + r0 * row_bytes, rows);
+            if (rcs[i] != TNTT_OK) msgs[i] = g_err;     // the message is thread-local: carry it over to the caller
+        });
+    }
+    for (std::thread &t : workers) t.join();
+    for (int i = 0; i < nplans; ++i)
+        if (rcs[i] != TNTT_OK) return fail(rcs[i], "device %d: %s", plans[i]->info.device, msgs[i].c_str());
     return TNTT_OK;
 }
 

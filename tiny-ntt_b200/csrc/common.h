@@ -70,4 +70,7 @@ cudaError_t launch_butterfly(const uint64_t *a, const uint64_t *b, const uint64_
 
 cudaError_t run_microbench(int kind, double *ops_per_second);
 
+// records the thread-local message tntt_last_error() returns; returns `code` (capi.cu)
+int api_fail(int code, const char *fmt, ...);
+
 }  // namespace tntt

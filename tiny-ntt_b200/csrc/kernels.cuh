@@ -23,6 +23,9 @@
 // Everything here is __host__ __device__ and takes the thread id as an argument so that
 // tests/host_emul.cpp can run the very same code on the CPU.
 #pragma once
+#if defined(TNTT_DEBUG_BOUNDS)
+#include <cassert>
+#endif
 #include "modarith.cuh"
 
 // how many twiddles (TG) / store-table entries (POST_GROUP) are fetched ahead of their use: Cfg::TG / Cfg::POST_GROUP
@@ -256,7 +259,10 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
             for (int j = 0; j < NJ; ++j) {
                 const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
 #pragma unroll
-                for (int a = 0; a < NA; ++a) ct_butterfly(x[a][k0], x[a][k1], tw[gi], mod);
+                for (int a = 0; a < NA; ++a) {
+                    if constexpr (RED == 3) ct_butterfly_barrett(x[a][k0], x[a][k1], tw[gi], mod);
+                    else ct_butterfly(x[a][k0], x[a][k1], tw[gi], mod);
+                }
             }
         }
     }
@@ -321,6 +327,7 @@ template <class C, int RED> TNTT_CX int fwd_out_bound() {
 // ... and of the pointwise product of two such spectra: Montgomery (red 0/1; u top-reduced first) u*v/2^BITS + q,
 // Solinas (red 2) below 2 q
 template <class C, int RED> TNTT_CX int pointwise_out_bound() {
+    if (RED == 3) return 1;
     if (RED == 2) return 2;
     constexpr int bf = fwd_out_bound<C, RED>();
     return ((bf > 8 ? 8 : bf) * bf + 15) / 16 + 1;
@@ -328,6 +335,7 @@ template <class C, int RED> TNTT_CX int pointwise_out_bound() {
 // rtl/ntt_pointwise_mult.v:17-42 on the registers of one thread: u, v = lazy spectra of a and b
 template <class C, int RED> TNTT_HD typename C::W pointwise_product(typename C::W u, typename C::W v, const Mod<typename C::W> &mod) {
     if constexpr (RED == 2) return solinas_mul(u, v);
+    else if constexpr (RED == 3) return barrett_mul(u, v, mod);   // rtl/ntt_pointwise_mult.v:17-42 as it is
     else {
         if (RED && fwd_out_bound<C, RED>() > 8) u = csub_top(u, mod.top_sub);  // u < 2^(BITS-1): no overflow
         return mont_mul(u, v, mod);   // the 2^-BITS is undone by the store table
@@ -347,7 +355,15 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
     constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
     if constexpr (B == 0 && dit_trivial_ok(RED, IN_BND)) {   // twiddle 1: no product at all
 #pragma unroll
-        for (int g = 0; g < NG; ++g) trivial_butterfly(x[2 * g], x[2 * g + 1], RED == 2 ? mod.q2 : mod.triv_c);
+        for (int g = 0; g < NG; ++g) {
+            if constexpr (RED == 3) {
+                trivial_butterfly(x[2 * g], x[2 * g + 1], mod.q);
+                x[2 * g] = csub(x[2 * g], mod.q);
+                x[2 * g + 1] = csub(x[2 * g + 1], mod.q);
+            } else {
+                trivial_butterfly(x[2 * g], x[2 * g + 1], RED == 2 ? mod.q2 : mod.triv_c);
+            }
+        }
     } else {
     if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
         reduce_top_x<C, kb, RED>(x, mod);
@@ -371,7 +387,8 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
-                ct_butterfly(x[k0], x[k1], tw[ji], mod);
+                if constexpr (RED == 3) ct_butterfly_barrett(x[k0], x[k1], tw[ji], mod);
+                else ct_butterfly(x[k0], x[k1], tw[ji], mod);
             }
         }
     }
@@ -637,81 +654,36 @@ __global__ void __launch_bounds__(C::THREADS, MINB)
 polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
                size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
                const __grid_constant__ Mod<typename C::W> mod) {
-    using W = typename C::W;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    W *tile = reinterpret_cast<W *>(smem_raw);
-    const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
-#if defined(TNTT_X_PERSISTENT)
-    // what-if: a grid of (SMs x CTAs per SM) persistent CTAs strides over the rows
-    for (size_t blk = blockIdx.x; blk * C::PPC < batch; blk += gridDim.x) {
-    const size_t poly = blk * C::PPC + pl;
-#else
-    const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
-#endif
-    const bool active = poly < batch;
-    const size_t off = active ? poly * C::N : 0;
-#if defined(TNTT_X_EMPTY_KERNEL)
-    if (batch) return;   // what-if only: launch overhead calibration
-#endif
+#include "polymul_body.inc"
+}
 
-    // shared memory: [NA tiles][stash tile][64 KB twiddle buffer][mbarrier]
-    TmaStage tma_s;
-    TmaStage *tma = nullptr;
-    const Tw<W> *stab = nullptr;
-    if constexpr (TMA) {
-        static_assert(C::NPASS >= 3 && C::PPC == 1, "TMA staging is built for the three-pass, one-polynomial-per-CTA shapes");
-        unsigned char *buf = smem_raw + ((size_t)NA * C::TILE + (size_t)STASH * C::PPC * C::N) * sizeof(W);
-        tma_s.init(buf + kTwBufBytes, buf);
-        tma = &tma_s;
-        stab = reinterpret_cast<const Tw<W> *>(buf);
-        if (threadIdx.x == 0) tma->issue(tb.fwd_last, (unsigned)(C::FWD_LAST_ENTRIES * sizeof(Tw<W>)));
-    }
+// ---------------------------------------------------------------------------------------------
+// Multi-modulus (RNS) batches, SURVEY.md section 8 f3 (reports/final-report.tex:1811-1817): operands [L][batch][N],
+// limb l holding the residues mod q_l.  ONE launch serves all limbs: blockIdx.y selects the limb's tables and
+// modulus constants from an array carried BY VALUE in the kernel parameters, so the uniform twiddles of the first
+// passes and the modulus constants stay constant-bank / uniform-register operands exactly as in the single-modulus
+// kernel (an index into the parameter block costs a uniform add).  16 limbs of 64-bit tables are 18 KB of the 32 KB
+// parameter space of sm_70+ under CUDA >= 12.1; more limbs take more launches (capi: tntt_rns_polymul).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRnsMaxLimbs = 16;
+template <typename W> struct RnsLimb {
+    PolymulTables<W> tb;
+    Mod<W> mod;
+};
+template <typename W> struct RnsLimbs { RnsLimb<W> limb[kRnsMaxLimbs]; };
 
-    W fa[C::R];
-    if constexpr (NA == 1) {
-        W x[1][C::R];
-        // STASH = 1: second shared tile; STASH = 2: the output row itself (global memory, stays in L2), which
-        // leaves the CTA with one tile of shared memory and the SM with a larger L1 for the twiddle tables
-        W *stash = (STASH == 2) ? (c + off + threadIdx.x) : (tile + NA * C::TILE + threadIdx.x);
-#if defined(TNTT_X_PREFETCH_B)
-        // b's row is needed one forward transform from now: pull it into L2 (one 128-byte line per thread)
-        if (threadIdx.x * 16 < C::N) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + off + threadIdx.x * 16));
-#endif
-        row_load<C>(x[0], a + off, tid, active);
-        forward_all<C, 1, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, true);
-#pragma unroll
-        for (int k = 0; k < C::R; ++k) {
-            if constexpr (STASH) stash[k * C::THREADS] = x[0][k];
-            else fa[k] = x[0][k];
-        }
-        row_load<C>(x[0], b + off, tid, active);
-        forward_all<C, 1, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, false);
-#pragma unroll
-        for (int k = 0; k < C::R; ++k) {
-            W u;
-            if constexpr (STASH) u = stash[k * C::THREADS];
-            else u = fa[k];
-#if defined(TNTT_X_NO_POINTWISE)
-            fa[k] = u ^ x[0][k];   // what-if only
-#else
-            fa[k] = pointwise_product<C, RED>(u, x[0][k], mod);
-#endif
-        }
-    } else {
-        W x[2][C::R];
-        row_load<C>(x[0], a + off, tid, active);
-        row_load<C>(x[1], b + off, tid, active);
-        forward_all<C, 2, RED, (TMA != 0)>(x, tile, pl, tid, tb, mod, tma, stab, true);
-#pragma unroll
-        for (int k = 0; k < C::R; ++k) {
-            fa[k] = pointwise_product<C, RED>(x[0][k], x[1][k], mod);
-        }
-    }
-    dit_all<C, RED, pointwise_out_bound<C, RED>(), (TMA != 0), C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod, tma, stab);
-    row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
-#if defined(TNTT_X_PERSISTENT)
-    }
-#endif
+template <class C, int NA, int RED, int MINB, int STASH = 0>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+polymul_rns_kernel(const typename C::W *a, const typename C::W *b, typename C::W *c, size_t batch,
+                   const __grid_constant__ RnsLimbs<typename C::W> limbs) {
+    constexpr int TMA = 0;
+    const PolymulTables<typename C::W> &tb = limbs.limb[blockIdx.y].tb;
+    const Mod<typename C::W> &mod = limbs.limb[blockIdx.y].mod;
+    const size_t limb_off = (size_t)blockIdx.y * batch * C::N;
+    a += limb_off;
+    b += limb_off;
+    c += limb_off;
+#include "polymul_body.inc"
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -886,6 +858,12 @@ __device__ __forceinline__ void cluster_exchange(typename C::W (&x)[C::R], typen
         const int E = C::template elem<LO_FROM>(gtid, k);
         const int g2 = ((E >> (LO_TO + C::LOGR)) << LO_TO) | (E & ((1 << LO_TO) - 1));   // next owner (row-wide thread id)
         const int k2 = (E >> LO_TO) & (C::R - 1);                                        // ... and its register
+#if defined(TNTT_DEBUG_BOUNDS)
+        // -DTNTT_DEBUG_BOUNDS build (make EXTRA=-DTNTT_DEBUG_BOUNDS; compute-sanitizer is closed on the GPU pool): the
+        // remote store must land in a CTA of this cluster, inside its N / CS-word buffer, in the slot its reader loads
+        assert(g2 >= 0 && g2 / T < CS && k2 * T + (g2 % T) < C::N / CS);
+        assert(C::template elem<LO_TO>(g2, k2) == E);
+#endif
         st_cluster<W>(base + (unsigned)((k2 * T + (g2 % T)) * sizeof(W)), (unsigned)(g2 / T), x[k]);
     }
     cluster_barrier();

@@ -262,13 +262,17 @@ template <typename W> TNTT_HD void trivial_butterfly(W &x, W &y, W c) {
 // Every register entering butterfly stage number `stage` (counted from the start of a transform whose inputs are
 // below `b0` units) is below bound_at(...) units; a stage whose outputs could pass 16 units first reduces its
 // un-multiplied inputs (the multiplied ones go through the product, which accepts any word).
+//   3: no lazy values at all -- the reference's own arithmetic: Barrett products of canonical operands
+//      (rtl/barrett_reduction.v:23-29) and fully reducing adds / subtracts (rtl/mod_add.v:14-15, mod_sub.v:15-17).
+//      Kept as a measured alternative (profiles/r02_variant_sweep.jsonl), not as a default: see DESIGN.md.
 TNTT_CX int reduce_result_bound(int red, int bound_in) { return red == 2 ? 2 : (bound_in - 7 > 8 ? bound_in - 7 : 8); }
 #if defined(TNTT_X_NO_REDUCE)
 TNTT_CX bool stage_needs_reduction(int, int, int) { return false; }   // what-if only: wrong results
 #else
-TNTT_CX bool stage_needs_reduction(int red, int g, int bound_in) { return red && bound_in + g > 16; }
+TNTT_CX bool stage_needs_reduction(int red, int g, int bound_in) { return (red == 1 || red == 2) && bound_in + g > 16; }
 #endif
 TNTT_CX int bound_after_stage(int red, int g, int bound_in) {
+    if (red == 3) return 1;   // canonical in, canonical out
     return (stage_needs_reduction(red, g, bound_in) ? reduce_result_bound(red, bound_in) : bound_in) + g;
 }
 TNTT_CX int bound_at(int red, int g, int b0, int stage) {
@@ -283,9 +287,10 @@ constexpr int kTrivMaxIn = 7;
 #if defined(TNTT_NO_TRIVIAL)
 TNTT_CX bool dit_trivial_ok(int, int) { return false; }
 #else
-TNTT_CX bool dit_trivial_ok(int red, int b0) { return !red || (red == 2 ? b0 <= 2 : b0 <= kTrivMaxIn); }
+TNTT_CX bool dit_trivial_ok(int red, int b0) { return !red || red == 3 || (red == 2 ? b0 <= 2 : b0 <= kTrivMaxIn); }
 #endif
 TNTT_CX int dit_bound_at(int red, int g, int b0, int stage) {
+    if (red == 3) return 1;
     if (!dit_trivial_ok(red, b0) || stage == 0) return bound_at(red, g, b0, stage);
     int b = red == 2 ? 2 * b0 : b0 + 8;
     for (int s = 1; s < stage; ++s) b = bound_after_stage(red, g, b);
@@ -397,6 +402,13 @@ TNTT_HD uint64_t barrett_mul(uint64_t a, uint64_t b, const Mod<uint64_t> &m) {
     uint64_t r = lo - q2 * m.q;
     r = csub(r, m.q);
     return csub(r, m.q);
+}
+
+// rtl/ntt_butterfly.v:43-72 literally: canonical (x, y) <- (x + w y mod q, x - w y mod q) with the Barrett product
+template <typename W> TNTT_HD void ct_butterfly_barrett(W &x, W &y, const Tw<W> &t, const Mod<W> &m) {
+    const W v = barrett_mul(y, t.w, m);
+    y = csub((W)(x - v + m.q), m.q);     // rtl/mod_sub.v:15-17
+    x = csub((W)(x + v), m.q);           // rtl/mod_add.v:14-15
 }
 
 }  // namespace tntt

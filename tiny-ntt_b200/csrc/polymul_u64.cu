@@ -26,6 +26,10 @@ static const PolymulVariant kVariants[] = {
     TNTT_POLYMUL_VARIANT_P(uint64_t, 64, 12, 4, 1, 2, 2, 2, 0),
     TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 12, 4, 1, 1, 2, 3, 1),
     TNTT_POLYMUL_VARIANT(uint64_t, 64, 12, 4, 1, 2, 2, 2),
+    // red3: the reference's own arithmetic (Barrett products with scripts/precompute_constants.py's k / mu, fully reducing
+    // adds) in the same fused kernel -- measured beside the Shoup / Solinas defaults, never a default itself
+    TNTT_POLYMUL_VARIANT_S(uint64_t, 64, 12, 4, 1, 1, 3, 3, 1),
+    TNTT_POLYMUL_VARIANT_P(uint64_t, 64, 12, 4, 1, 2, 3, 2, 0),
     // small batches: one row per cluster of 4 CTAs, exchanges through distributed shared memory
     TNTT_POLYMUL_CLUSTER(uint64_t, 64, 12, 3, 4, 1),
     TNTT_POLYMUL_CLUSTER(uint64_t, 64, 12, 3, 4, 0),

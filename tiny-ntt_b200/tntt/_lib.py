@@ -21,6 +21,9 @@ SYMBOLS = (
     "tntt_variant_describe", "tntt_variant_matches", "tntt_polymul_variant", "tntt_plan_set_default_variant",
     "tntt_microbench", "tntt_last_error", "tntt_version",
     "tntt_spectrum_forward", "tntt_spectrum_inverse", "tntt_polymul_spectrum", "tntt_plan_info_size",
+    "tntt_rns_plan_create", "tntt_rns_plan_destroy", "tntt_rns_plan_limbs", "tntt_rns_plan_word_bytes",
+    "tntt_rns_plan_kernel", "tntt_rns_plan_table_bytes", "tntt_rns_polymul", "tntt_rns_plan_check_tables",
+    "tntt_rns_kernel_attributes", "tntt_find_psi", "tntt_polymul_host_multi",
 )
 
 
@@ -66,6 +69,7 @@ def lib() -> C.CDLL:
     L.tntt_pointwise.argtypes = [vp, vp, vp, vp, sz, vp]
     L.tntt_polymul.argtypes = [vp, vp, vp, vp, sz, vp]
     L.tntt_polymul_host.argtypes = [vp, vp, vp, vp, sz]
+    L.tntt_polymul_host_multi.argtypes = [C.POINTER(vp), i, vp, vp, vp, sz]
     L.tntt_spectrum_forward.argtypes = [vp, vp, vp, sz, vp]
     L.tntt_spectrum_inverse.argtypes = [vp, vp, vp, sz, vp]
     L.tntt_polymul_spectrum.argtypes = [vp, vp, vp, vp, sz, sz, vp]
@@ -80,6 +84,18 @@ def lib() -> C.CDLL:
     L.tntt_polymul_variant.argtypes = [vp, i, vp, vp, vp, sz, vp]
     L.tntt_plan_set_default_variant.argtypes = [vp, i]
     L.tntt_microbench.argtypes = [i, i, C.POINTER(C.c_double)]
+    L.tntt_rns_plan_create.argtypes = [C.POINTER(vp), i, u32, C.POINTER(u64), C.POINTER(u64), i]
+    L.tntt_rns_plan_destroy.argtypes = [vp]
+    L.tntt_rns_plan_destroy.restype = None
+    L.tntt_rns_plan_limbs.argtypes = L.tntt_rns_plan_word_bytes.argtypes = [vp]
+    L.tntt_rns_plan_kernel.argtypes = [vp]
+    L.tntt_rns_plan_kernel.restype = C.c_char_p
+    L.tntt_rns_plan_table_bytes.argtypes = [vp]
+    L.tntt_rns_plan_table_bytes.restype = sz
+    L.tntt_rns_polymul.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.tntt_rns_plan_check_tables.argtypes = [vp, i]
+    L.tntt_rns_kernel_attributes.argtypes = [vp, C.POINTER(i), C.POINTER(sz), C.POINTER(i)]
+    L.tntt_find_psi.argtypes = [u32, u64, u64, C.POINTER(u64)]
     L.tntt_last_error.restype = C.c_char_p
     L.tntt_version.restype = i
     L.tntt_plan_info_size.restype = sz

@@ -7,7 +7,7 @@ current torch CUDA stream and is asynchronous like any torch op.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import Optional, Sequence
 
 from . import _lib
 from ._lib import TNTT_REDUCE_INPUT, TNTT_TWIST, check, lib
@@ -148,8 +148,40 @@ def polymul_host(plan: Plan, a, b, out=None):
     if ta.shape != tb.shape or ta.shape[-1] != plan.n:
         raise ValueError(f"Expected {plan.n} coefficients")
     ta, tb = ta.contiguous(), tb.contiguous()
-    o = torch.empty_like(ta, pin_memory=ta.is_pinned()) if out is None else out
+    o = _host_out(ta, out)
     check(lib().tntt_polymul_host(plan._h, ta.data_ptr(), tb.data_ptr(), o.data_ptr(), _rows(ta)))
+    return o
+
+
+def _host_out(t, out):
+    import torch
+
+    if out is None:
+        return torch.empty_like(t, pin_memory=t.is_pinned())
+    if out.is_cuda or out.shape != t.shape or out.dtype != t.dtype or not out.is_contiguous():
+        raise ValueError("out must be a contiguous host tensor of the input's shape and dtype")
+    return out
+
+
+def polymul_sharded(plans: Sequence[Plan], a, b, out=None):
+    """The host-buffer product over several GPUs from this one process (tntt_polymul_host_multi): plans[i] -- plans
+    of the same ring on distinct devices, e.g. ``get_plans(n, q, psi)`` -- takes the i-th contiguous range of
+    ceil(B / len(plans)) rows; per-device plan, streams and staging buffers, one host thread per device, host
+    barrier at the end, no collective.  Host tensors in (pin them), host tensor out."""
+    ta, tb = as_tensor(a), as_tensor(b)
+    if not plans:
+        raise ValueError("need at least one plan")
+    plan = plans[0]
+    if ta.is_cuda or tb.is_cuda:
+        raise ValueError("polymul_sharded takes host tensors")
+    if ta.dtype not in plan.torch_dtypes or tb.dtype != ta.dtype:
+        raise TypeError(f"host tensors must have dtype in {plan.torch_dtypes}")
+    if ta.shape != tb.shape or ta.shape[-1] != plan.n:
+        raise ValueError(f"Expected {plan.n} coefficients")
+    ta, tb = ta.contiguous(), tb.contiguous()
+    o = _host_out(ta, out)
+    handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    check(lib().tntt_polymul_host_multi(handles, len(plans), ta.data_ptr(), tb.data_ptr(), o.data_ptr(), _rows(ta)))
     return o
 
 
@@ -158,7 +190,9 @@ def cg_stage(plan: Plan, x, stage: int, inverse_root: bool = False, out=None):
     import torch
 
     t = _prep(plan, x, "x")
-    o = torch.empty_like(t) if out is None else out
+    o = _out_like(t, out)
+    if o.data_ptr() == t.data_ptr():
+        raise ValueError("cg_stage is out of place: out must not alias x")
     check(lib().tntt_cg_stage(plan._h, t.data_ptr(), o.data_ptr(), _rows(t), stage, int(inverse_root), _stream(plan)))
     return o
 
@@ -167,7 +201,9 @@ def bit_reverse(plan: Plan, x, out=None):
     import torch
 
     t = _prep(plan, x, "x")
-    o = torch.empty_like(t) if out is None else out
+    o = _out_like(t, out)
+    if o.data_ptr() == t.data_ptr():
+        raise ValueError("bit_reverse is out of place: out must not alias x")
     check(lib().tntt_bit_reverse(plan._h, t.data_ptr(), o.data_ptr(), _rows(t), _stream(plan)))
     return o
 

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 from . import _lib
 from ._lib import PlanInfo, TnttError, check, lib
@@ -113,6 +113,14 @@ def get_plan(n: int, q: int, root: int, root_is_psi: bool = True, device: Option
             plan = Plan.create(n, q, root, root_is_psi, dev)
             _cache[key] = plan
         return plan
+
+
+def get_plans(n: int, q: int, root: int, root_is_psi: bool = True, devices: Optional[Sequence[int]] = None) -> List[Plan]:
+    """One cached plan per device (default: every visible GPU) for the single-process multi-GPU entry points
+    (ops.polymul_sharded / tntt_polymul_host_multi)."""
+    torch = _require_cuda()
+    devs = list(range(torch.cuda.device_count())) if devices is None else [int(d) for d in devices]
+    return [get_plan(n, q, root, root_is_psi, d) for d in devs]
 
 
 def clear_plan_cache() -> None:
