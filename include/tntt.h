@@ -38,10 +38,10 @@ extern "C" {
 enum tntt_status {
     TNTT_OK = 0,
     TNTT_BAD_ARG = -1,        /* null pointer, bad flag, misaligned buffer */
-    TNTT_BAD_ROOT = -2,       /* root is not a primitive 2n-th (psi) / n-th (omega) root of unity mod q */
+    TNTT_BAD_ROOT = -2,       /* root not reduced mod q (tntt_find_psi: no root exists) */
     TNTT_UNSUPPORTED_N = -3,  /* n is not a power of two in [2, 65536] */
     TNTT_CUDA_ERROR = -4,
-    TNTT_UNSUPPORTED_Q = -5,  /* q even, q < 3 or q >= 2^60 */
+    TNTT_UNSUPPORTED_Q = -5,  /* q < 2 or q >= 2^60 (RNS plans: not an odd prime) */
     TNTT_IO_ERROR = -6,       /* hex table file unreadable or malformed */
     TNTT_NO_DEVICE = -7       /* no CUDA device: there is no CPU path */
 };
@@ -76,6 +76,9 @@ typedef struct tntt_plan_info {
     int cluster_variant, cluster_batch_max;
     int small_variant, small_batch_max;
     int spectrum;              /* 1: tntt_spectrum_forward / _inverse / tntt_polymul_spectrum are available */
+    int literal_only;          /* 1: q is not an odd prime, or the root is not primitive (psi^n != -1, omega = 0): the
+                                * plan runs the reference's literal stage schedule only (cg_ntt.py:29-92 accepts any
+                                * integers; so does this), no fused / transform-domain kernels */
     int solinas;               /* 1: q = 2^60 - 2^14 + 1 (rtl/ntt_poly_mult.sv:16-26): the fused kernels may use its
                                 * shift-and-add reductions (variants "red2") instead of the generic lazy ones */
 } tntt_plan_info;

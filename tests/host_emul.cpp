@@ -231,7 +231,7 @@ int run_polymul(const void *a, const void *b, void *c, size_t batch, uint64_t q,
 
 // mode 0: spec = forward(a), out = inverse(spec); 1: out = polymul_spectrum(a, forward(b)), one spectrum per row;
 // 2: the same with the spectrum of b's row 0 shared by the batch; 3: out = forward(a) (the raw spectrum)
-template <class C, bool RED>
+template <class C, int RED>
 int run_spectrum(const void *a, const void *b, void *out, size_t batch, uint64_t q, uint64_t psi, int mode) {
     using W = typename C::W;
     constexpr int BITS = WordTraits<W>::BITS;
@@ -242,10 +242,11 @@ int run_spectrum(const void *a, const void *b, void *out, size_t batch, uint64_t
     auto inv = host::dit_pyramid<W>(host::modinv(omega, q), C::N, q);
     auto post_mont = host::scaled_powers<W>(host::modinv(psi, q), host::mulmod(n_inv, (uint64_t)((((host::u128)1) << BITS) % q), q), C::N, q);
     auto post_plain = host::scaled_powers<W>(host::modinv(psi, q), n_inv, C::N, q);
+    if (RED == 2 && q != kSolinasQ) return -2;
     Emu<C, 1, RED> e;
     e.tb.fwd_pyr = fwd.data();
     e.tb.fwd_last = last.data();
-    e.tb.post = post_mont.data();
+    e.tb.post = RED == 2 ? post_plain.data() : post_mont.data();   // the Solinas pointwise product leaves no 2^-BITS
     e.tb.inv.pyr = inv.data();
     for (int i = 0; i < MAX_R && i < C::N; ++i) { e.tb.fwd_head[i] = fwd[i]; e.tb.inv.head[i] = inv[i]; }
     e.mod = host::make_mod<W>(q, C::LOGN);
@@ -308,7 +309,7 @@ int run_transform(const void *in, void *out, size_t batch, uint64_t q, uint64_t 
 
 #define SPEC_CASE(WB, WT, LN, LR, PPC, RED_)                                                           \
     if (word_bytes == WB && logn == LN && logr == LR && ppc == PPC && red == RED_)                    \
-        return run_spectrum<Cfg<WT, LN, LR, PPC>, (RED_ != 0)>(a, b, out, batch, q, psi, mode);
+        return run_spectrum<Cfg<WT, LN, LR, PPC>, RED_>(a, b, out, batch, q, psi, mode);
 
 extern "C" {
 
@@ -324,6 +325,7 @@ int emu_spectrum(int word_bytes, int logn, int logr, int ppc, int red, const voi
     SPEC_CASE(8, uint64_t, 10, 4, 4, 1)
     SPEC_CASE(8, uint64_t, 12, 4, 1, 0)
     SPEC_CASE(8, uint64_t, 12, 4, 1, 1)
+    SPEC_CASE(8, uint64_t, 12, 4, 1, 2)
     SPEC_CASE(4, uint32_t, 9, 5, 16, 0)
     SPEC_CASE(4, uint32_t, 11, 4, 2, 0)
     SPEC_CASE(4, uint32_t, 13, 5, 1, 0)

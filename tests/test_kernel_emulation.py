@@ -314,3 +314,25 @@ def test_emulated_barrett_shapes(logn, logr, ppc, na, pad, tag, co):
     a[0], b[0] = q - 1, q - 1
     want = co.nwc_poly_mult(a, b, psi, q, threads=4)
     assert (emu.polymul(8, logn, logr, ppc, na, 3, a, b, q, psi, pad=pad).astype(np.uint64) == want).all()
+
+
+def test_emulated_solinas_transform_domain_kernels(co):
+    """sp_u64_n12_r4_p1_red2: the transform-domain kernels with the Solinas reductions (the 60-bit prime only)"""
+    p = O.PARAMS["n4096_60"]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    rng = np.random.default_rng(77)
+    a = rng.integers(0, q, size=(3, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(3, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    args = (8, 12, 4, 1, 2, a, b, q, psi)
+    assert (emu.spectrum(*args, 0).astype(np.uint64) == a).all()
+    assert (emu.spectrum(*args, 1).astype(np.uint64) == want).all()
+    shared = co.nwc_poly_mult(a, np.broadcast_to(b[0], b.shape).copy(), psi, q, threads=4)
+    assert (emu.spectrum(*args, 2).astype(np.uint64) == shared).all()
+    # the spectrum itself is the same canonical row whichever reduction mode produced it
+    assert (emu.spectrum(*args, 3) == emu.spectrum(8, 12, 4, 1, 1, a, b, q, psi, 3)).all()
+    omega = psi * psi % q
+    assert (emu.spectrum(*args, 5).astype(np.uint64) == co.cg_ntt(a, omega, q)).all()
+    assert (emu.spectrum(*args, 7).astype(np.uint64) == co.cg_intt(a, omega, q)).all()
+    assert emu.lib().emu_range_violations() == 0

@@ -168,3 +168,22 @@ def test_oracle_matches_the_reference_refs_twins():
         x = [v % q for v in c["x"]]
         assert O.cg_ntt(x, omega, q) == c["forward"]
         assert O.cg_intt(x, omega, q) == c["inverse"]
+
+
+def test_oracle_follows_the_reference_outside_the_ntt_friendly_domain():
+    """Even / composite moduli, non-primitive roots, omega = 0: outputs of the reference's own cg_ntt.py
+    (tests/golden/make_golden_domain.py) against the oracle's restatement."""
+    import json
+    import os
+
+    from oracle import ntt_oracle as O
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_domain.json")
+    with open(path) as fh:
+        cases = json.load(fh)["cases"]
+    assert len(cases) >= 8
+    for c in cases:
+        assert O.cg_ntt(c["a"], c["omega"], c["q"]) == c["cg_ntt"], c["note"]
+        assert O.cg_intt(c["a"], c["omega"], c["q"]) == c["cg_intt"], c["note"]
+        assert O.cg_intt(c["cg_ntt"], c["omega"], c["q"]) == c["roundtrip"], c["note"]
+        assert O.nwc_poly_mult(c["a"], c["b"], c["psi"], c["q"]) == c["nwc_poly_mult"], c["note"]

@@ -148,7 +148,7 @@ template <typename W> int build_tables(tntt_plan *p) {
         CUDA_TRY(upload(fw, &p->omega_pow));
         CUDA_TRY(upload(bw, &p->omega_inv_pow));
     }
-    if (p->info.has_psi) {
+    if (p->info.has_psi && !p->info.literal_only) {   // tables of the fused kernels
         std::vector<Tw<W>> fwd = host::fwd_pyramid<W>(p->info.psi, n, q);
         CUDA_TRY(upload(fwd, &p->fwd_pyr));
         keep_head(fwd, 0);
@@ -158,6 +158,8 @@ template <typename W> int build_tables(tntt_plan *p) {
         const uint64_t r_mod_q = (uint64_t)((((host::u128)1) << BITS) % q);
         CUDA_TRY(upload(host::scaled_powers<W>(p->info.psi_inv, host::mulmod(p->info.n_inv, r_mod_q, q), n, q),
                         &p->post_mont));
+    }
+    if (p->info.has_psi) {   // the twist tables of cg_ntt.py:82-83,92 (any modulus)
         CUDA_TRY(upload(host::scaled_powers<W>(p->info.psi, 1, n, q), &p->pre_twist));
         CUDA_TRY(upload(host::scaled_powers<W>(p->info.psi_inv, p->info.n_inv, n, q), &p->post_untwist));
     }
@@ -231,12 +233,16 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
     }
     if (device < 0 || device >= ndev) return fail(TNTT_BAD_ARG, "device %d out of range (0..%d)", device, ndev - 1);
     if (n < 2 || n > 65536 || (n & (n - 1))) return fail(TNTT_UNSUPPORTED_N, "n=%u must be a power of two in [2, 65536]", n);
-    if (q < 3 || !(q & 1) || q >= (1ull << 60)) return fail(TNTT_UNSUPPORTED_Q, "q=%llu must be odd, >= 3 and < 2^60", (unsigned long long)q);
-    if (!host::is_prime(q)) return fail(TNTT_UNSUPPORTED_Q, "q=%llu is not prime", (unsigned long long)q);
+    if (q < 2 || q >= (1ull << 60)) return fail(TNTT_UNSUPPORTED_Q, "q=%llu must be in [2, 2^60)", (unsigned long long)q);
     if (root >= q) return fail(TNTT_BAD_ROOT, "root must be reduced mod q");
-    if (root_is_psi && !host::is_primitive_2n_root(root, n, q))
-        return fail(TNTT_BAD_ROOT, "psi=%llu: psi^%u != -1 mod q", (unsigned long long)root, n);
-    if (!root_is_psi && root == 0) return fail(TNTT_BAD_ROOT, "omega must be non-zero");
+    // new_reference/cg_ntt.py:29-92 never looks at its modulus or roots: `% modulus` after every operation and
+    // modinv = pow(a, q - 2, q) give well-defined numbers for ANY integers, whether or not they are a transform of
+    // anything.  The fast kernels (Shoup / Montgomery tables, merged-psi passes) need an odd prime q and primitive
+    // roots; everything else -- even or composite q, psi with psi^n != -1, omega = 0 -- gets a LITERAL plan that runs
+    // the reference's stage schedule as it is written (tntt_cg_stage kernels, Barrett products, the same Fermat-style
+    // "inverses"), so the drop-in returns the reference's numbers there too.
+    const bool field = q >= 3 && (q & 1) && host::is_prime(q);
+    const bool literal = !field || (root_is_psi ? !host::is_primitive_2n_root(root, n, q) : root == 0);
 
     DeviceSetter ds(device);
     if (!ds.ok) return fail(TNTT_CUDA_ERROR, "cudaSetDevice(%d) failed", device);
@@ -252,7 +258,8 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
     I.psi_inv = root_is_psi ? host::modinv(root, q) : 0;
     I.omega = root_is_psi ? host::mulmod(root, root, q) : root;
     I.omega_inv = host::modinv(I.omega, q);
-    I.omega_is_primitive = host::is_primitive_n_root(I.omega, n, q) ? 1 : 0;
+    I.omega_is_primitive = (!literal && host::is_primitive_n_root(I.omega, n, q)) ? 1 : 0;
+    I.literal_only = literal ? 1 : 0;
     I.n_inv = host::modinv(n % q, q);
     // uint32 coefficients when the whole transform fits the lazy 32-bit range, else uint64
     I.word_bytes = host::lazy_full_ok<uint32_t>(q, (int)I.logn) ? 4 : 8;
@@ -288,7 +295,8 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
         int c = 0;
         const SpectrumVariant *sv = spectrum_variants(&c);
         for (int i = 0; i < c; ++i)
-            if (sv[i].word_bytes == I.word_bytes && sv[i].logn == (int)I.logn && sv[i].red == I.lazy_reduce && p->cyc_ct_last[sv[i].logr]) {
+            if (sv[i].word_bytes == I.word_bytes && sv[i].logn == (int)I.logn && p->cyc_ct_last[sv[i].logr] &&
+                (sv[i].red == 2 ? (I.lazy_reduce && I.solinas) : sv[i].red == I.lazy_reduce)) {
                 if (sv[i].red && !host::lazy_pass_ok<uint64_t>(q, sv[i].logr)) continue;
                 cudaError_t e = sv[i].prepare();
                 if (e != cudaSuccess) { tntt_plan_destroy(p); return fail(TNTT_CUDA_ERROR, "prepare %s: %s", sv[i].name, cudaGetErrorString(e)); }
@@ -423,6 +431,7 @@ template <typename W> int spectrum_op(const tntt_plan *p, int op, const void *a,
                                       size_t b_stride, cudaStream_t st) {
     PolymulTables<W> tb;
     fill_polymul_tables<W>(p, p->spectrum->logr, tb);
+    if (p->spectrum->red == 2) tb.post = (const Tw<W> *)p->post_untwist;   // Solinas pointwise product: no 2^-BITS to undo
     cudaError_t e = cudaSuccess;
     if (op == 0) e = p->spectrum->forward(a, out, batch, &tb, p->mod(), st);
     else if (op == 1) e = p->spectrum->inverse(a, out, batch, &tb, p->post_untwist, p->mod(), st);
@@ -585,7 +594,7 @@ int tntt_variant_describe(int variant, char *buf, size_t buflen) {
 int tntt_variant_matches(const tntt_plan *p, int variant) {
     if (!p || variant < 0 || variant >= tntt_variant_count()) return 0;
     const PolymulVariant &v = all_variants()[variant];
-    if (!p->info.has_psi || v.word_bytes != p->info.word_bytes || v.logn != (int)p->info.logn) return 0;
+    if (!p->info.has_psi || p->info.literal_only || v.word_bytes != p->info.word_bytes || v.logn != (int)p->info.logn) return 0;
     // red 2 = the Solinas-form reductions: an alternative to red 1 for the one modulus they are written for
     // red 3 = Barrett products of canonical values: serves every modulus of the 64-bit paths
     if (v.red == 3) return v.word_bytes == 8 ? 1 : 0;

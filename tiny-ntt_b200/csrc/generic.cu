@@ -48,14 +48,14 @@ bit_reverse_kernel(const W *__restrict__ in, W *__restrict__ out, size_t batch, 
 
 template <typename W>
 __global__ void __launch_bounds__(kThreads)
-pointwise_kernel(const W *__restrict__ a, const W *__restrict__ b, W *__restrict__ c, size_t count, Mod<W> mod) {
+pointwise_kernel(const W *a, const W *b, W *c, size_t count, Mod<W> mod) {   // c may alias a or b (in place)
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x)
         c[idx] = barrett_mul(a[idx], b[idx], mod);
 }
 
 template <typename W>
 __global__ void __launch_bounds__(kThreads)
-mul_table_kernel(const W *__restrict__ in, W *__restrict__ out, size_t batch, int logn, const Tw<W> *__restrict__ table,
+mul_table_kernel(const W *in, W *out, size_t batch, int logn, const Tw<W> *__restrict__ table,   // in == out allowed
                  Mod<W> mod) {
     const size_t n = (size_t)1 << logn, total = batch * n;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -66,15 +66,15 @@ mul_table_kernel(const W *__restrict__ in, W *__restrict__ out, size_t batch, in
 
 template <typename W>
 __global__ void __launch_bounds__(kThreads)
-scale_kernel(const W *__restrict__ in, W *__restrict__ out, size_t count, W w, W wp, Mod<W> mod) {
+scale_kernel(const W *in, W *out, size_t count, W w, W wp, Mod<W> mod) {   // in == out allowed
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x)
         out[idx] = csub(shoup_mul(in[idx], w, wp, mod.nq), mod.q);
 }
 
 // 8-lane (or any-lane) butterfly batch of new_reference/cg_ntt_8butterfly.py:8-27 / rtl/ntt_butterfly.v:43-72
 __global__ void __launch_bounds__(kThreads)
-butterfly_kernel(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, const uint64_t *__restrict__ w,
-                 uint64_t *__restrict__ out_a, uint64_t *__restrict__ out_b, size_t count, Mod<uint64_t> mod) {
+butterfly_kernel(const uint64_t *a, const uint64_t *b, const uint64_t *w, uint64_t *out_a, uint64_t *out_b, size_t count,
+                 Mod<uint64_t> mod) {   // outputs may alias inputs
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x) {
         const uint64_t t = barrett_mul(w[idx], b[idx], mod), left = a[idx];
         const uint64_t s = left + t;

@@ -231,6 +231,11 @@ TNTT_HD void fwd_stage(typename C::W (&x)[NA][C::R], int tid, const PolymulTable
 #pragma unroll
         for (int a = 0; a < NA; ++a) reduce_top_x<C, kb, RED>(x[a], mod);
     }
+#if !defined(TNTT_X_NO_REDUCE)
+    // with RED set the tracked bound (units of 2^(BITS-4), or of q for RED 2) must stay within the word after every stage
+    static_assert(RED == 0 || bound_after_stage(RED, Growth<W>::G, bound_at(RED, Growth<W>::G, 1, s)) <= 16,
+                  "forward stage: lazy values could pass 2^BITS");
+#endif
     // twiddles are fetched TG at a time, ahead of their butterflies, so that their latencies overlap
     constexpr int TG = NG < C::TG ? NG : C::TG;
 #pragma unroll
@@ -367,6 +372,10 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
     } else {
     if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
         reduce_top_x<C, kb, RED>(x, mod);
+#if !defined(TNTT_X_NO_REDUCE)
+    static_assert(RED == 0 || bound_after_stage(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)) <= 16,
+                  "inverse stage: lazy values could pass 2^BITS");
+#endif
     constexpr int TG = NJ < C::TG ? NJ : C::TG;
 #pragma unroll
     for (int j0 = 0; j0 < NJ; j0 += TG) {
@@ -651,7 +660,7 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
 //   TMA = 1: the per-thread twiddle tables are staged in shared memory by bulk async copies (see TmaStage)
 template <class C, int NA, int RED, int MINB, int STASH = 0, int TMA = 0>
 __global__ void __launch_bounds__(C::THREADS, MINB)
-polymul_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
+polymul_kernel(const typename C::W *a, const typename C::W *b, typename C::W *c,   // c may alias a or b: no __restrict__
                size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
                const __grid_constant__ Mod<typename C::W> mod) {
 #include "polymul_body.inc"
@@ -706,7 +715,7 @@ polymul_rns_kernel(const typename C::W *a, const typename C::W *b, typename C::W
 // decide the transform: merged-psi pyramid = ntt(twist(.)), cyclic pyramid (host::fwd_pyramid_cyclic) = cg_ntt.
 template <class C, int RED, int MINB, bool NATURAL = false>
 __global__ void __launch_bounds__(C::THREADS, MINB)
-spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
+spectrum_forward_kernel(const typename C::W *in, typename C::W *out, size_t batch,
                         const __grid_constant__ PolymulTables<typename C::W> tb,
                         const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
@@ -749,7 +758,7 @@ spectrum_forward_kernel(const typename C::W *__restrict__ in, typename C::W *__r
 // by the one factor `post_uniform` (N^-1: cg_intt)
 template <class C, int RED, int MINB, bool NATURAL = false, bool TABLE = true>
 __global__ void __launch_bounds__(C::THREADS, MINB)
-spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
+spectrum_inverse_kernel(const typename C::W *in, typename C::W *out, size_t batch,
                         const __grid_constant__ DitTables<typename C::W> inv, const Tw<typename C::W> *__restrict__ post,
                         const Tw<typename C::W> post_uniform, const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
@@ -783,8 +792,7 @@ spectrum_inverse_kernel(const typename C::W *__restrict__ in, typename C::W *__r
 // b_stride = N: one spectrum per row; b_stride = 0: one spectrum shared by the whole batch
 template <class C, int RED, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB)
-polymul_spectrum_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ bspec,
-                        typename C::W *__restrict__ c, size_t batch, size_t b_stride,
+polymul_spectrum_kernel(const typename C::W *a, const typename C::W *bspec, typename C::W *c, size_t batch, size_t b_stride,
                         const __grid_constant__ PolymulTables<typename C::W> tb,
                         const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
@@ -899,7 +907,7 @@ __device__ __forceinline__ void cluster_inverse_rest(typename C::W (&x)[C::R], t
 // launched with a cluster dimension of CS (cudaLaunchKernelEx); grid = rows * CS CTAs of P / CS threads
 template <class C, int CS, int RED, int MINB = 1>
 __global__ void __launch_bounds__(C::P / CS, MINB)
-polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
+polymul_cluster_kernel(const typename C::W *a, const typename C::W *b, typename C::W *c,
                        size_t batch, const __grid_constant__ PolymulTables<typename C::W> tb,
                        const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
@@ -946,7 +954,7 @@ polymul_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W 
 // the row-wide thread index (cluster rank * threads + threadIdx).
 template <class C, int CS, int RED, int MINB, int MODE>
 __global__ void __launch_bounds__(C::P / CS, MINB)
-spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W *__restrict__ b, typename C::W *__restrict__ c,
+spectrum_cluster_kernel(const typename C::W *a, const typename C::W *b, typename C::W *c,
                         size_t batch, size_t b_stride, const __grid_constant__ PolymulTables<typename C::W> tb,
                         const Tw<typename C::W> *__restrict__ post, const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;
@@ -1002,7 +1010,7 @@ spectrum_cluster_kernel(const typename C::W *__restrict__ a, const typename C::W
 // ---------------------------------------------------------------------------------------------
 template <class C, int RED, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB)
-transform_kernel(const typename C::W *__restrict__ in, typename C::W *__restrict__ out, size_t batch,
+transform_kernel(const typename C::W *in, typename C::W *out, size_t batch,
                  const __grid_constant__ TransformTables<typename C::W> tb,
                  const __grid_constant__ Mod<typename C::W> mod) {
     using W = typename C::W;

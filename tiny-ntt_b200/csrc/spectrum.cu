@@ -4,7 +4,7 @@
 
 namespace tntt {
 
-template <class C, bool RED, int MINB> struct SpectrumInst {
+template <class C, int RED, int MINB> struct SpectrumInst {
     using W = typename C::W;
     static constexpr size_t SMEM = (size_t)C::PPC * C::N * sizeof(W);
     static unsigned ctas(size_t batch) { return (unsigned)((batch + C::PPC - 1) / C::PPC); }
@@ -59,7 +59,7 @@ template <class C, bool RED, int MINB> struct SpectrumInst {
 };
 
 // rows on a thread-block cluster (N = 16384, 32768): spectrum order only, no natural-order kernels
-template <class C, int CS, bool RED, int MINB> struct SpectrumClusterInst {
+template <class C, int CS, int RED, int MINB> struct SpectrumClusterInst {
     using W = typename C::W;
     static constexpr size_t SMEM = 2 * (size_t)(C::N / CS) * sizeof(W);
     template <int MODE>
@@ -103,21 +103,21 @@ template <class C, int CS, bool RED, int MINB> struct SpectrumClusterInst {
 #define TNTT_SPECTRUM_CLUSTER(WT, WB, LN, LR, CS, RED, MINB)                                                 \
     SpectrumVariant {                                                                                        \
         "sp_u" #WB "_n" #LN "_r" #LR "_red" #RED "_c" #CS, WB / 8, LN, LR, 1, RED,                              \
-            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::forward,                           \
-            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::inverse,                           \
-            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::polymul,                           \
-            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, (RED != 0), MINB>::prepare, nullptr, nullptr          \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::forward,                           \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::inverse,                           \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::polymul,                           \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::prepare, nullptr, nullptr          \
     }
 
 #define TNTT_SPECTRUM_VARIANT(WT, WB, LN, LR, PPC, RED, MINB)                                                \
     SpectrumVariant {                                                                                        \
         "sp_u" #WB "_n" #LN "_r" #LR "_p" #PPC "_red" #RED, WB / 8, LN, LR, PPC, RED,                          \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::forward,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::inverse,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::polymul,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::prepare,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::forward_natural,                           \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, (RED != 0), MINB>::inverse_natural                            \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::forward,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::inverse,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::polymul,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::prepare,                                   \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::forward_natural,                           \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::inverse_natural                            \
     }
 
 // one shape per (word, N, reduction mode): the spectrum order is part of the plan, not of a kernel variant
@@ -130,6 +130,7 @@ static const SpectrumVariant kVariants[] = {
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 10, 4, 4, 0, 2),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 10, 4, 4, 1, 2),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 12, 4, 1, 0, 2),
+    TNTT_SPECTRUM_VARIANT(uint64_t, 64, 12, 4, 1, 2, 3),     // q = 2^60 - 2^14 + 1 only (Solinas reductions): listed before red1
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 12, 4, 1, 1, 3),
     // N = 512, 2048, 8192
     TNTT_SPECTRUM_VARIANT(uint32_t, 32, 9, 5, 16, 0, 2),

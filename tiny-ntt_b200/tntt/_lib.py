@@ -34,7 +34,7 @@ class PlanInfo(C.Structure):
         ("barrett_k", C.c_int), ("barrett_mu", C.c_uint64), ("has_psi", C.c_int), ("omega_is_primitive", C.c_int),
         ("fused", C.c_int), ("lazy_reduce", C.c_int), ("default_variant", C.c_int), ("device", C.c_int),
         ("cluster_variant", C.c_int), ("cluster_batch_max", C.c_int), ("small_variant", C.c_int),
-        ("small_batch_max", C.c_int), ("spectrum", C.c_int), ("solinas", C.c_int),
+        ("small_batch_max", C.c_int), ("spectrum", C.c_int), ("literal_only", C.c_int), ("solinas", C.c_int),
     ]
 
 
