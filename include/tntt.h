@@ -187,6 +187,15 @@ size_t tntt_rns_plan_table_bytes(const tntt_rns_plan *plan);       /* device mem
 /* c[l] = a[l] * b[l] in Z_{q_l}[x]/(x^n+1) for every limb: ONE kernel launch per 16 limbs (the limb index is
  * blockIdx.y; tables and modulus constants are picked out of the kernel parameters). */
 int tntt_rns_polymul(const tntt_rns_plan *plan, const void *a, const void *b, void *c, size_t batch, void *cuda_stream);
+/* Operands kept in the transform domain, all limbs per launch (the multi-modulus forms of tntt_spectrum_forward /
+ * tntt_spectrum_inverse / tntt_polymul_spectrum / tntt_pointwise): spectra are [limbs][batch][n], canonical, in the
+ * spectrum order of the plan's kernel shape; b_spectrum is [limbs][b_rows][n] with b_rows = batch or 1 (one spectrum
+ * per limb shared by the whole batch). */
+int tntt_rns_spectrum_forward(const tntt_rns_plan *plan, const void *in, void *out, size_t batch, void *cuda_stream);
+int tntt_rns_spectrum_inverse(const tntt_rns_plan *plan, const void *in, void *out, size_t batch, void *cuda_stream);
+int tntt_rns_polymul_spectrum(const tntt_rns_plan *plan, const void *a, const void *b_spectrum, void *c, size_t batch,
+                              size_t b_rows, void *cuda_stream);
+int tntt_rns_pointwise(const tntt_rns_plan *plan, const void *a, const void *b, void *c, size_t batch, void *cuda_stream);
 /* test hook: regenerates limb `limb`'s tables with the host generators and compares them word for word with the
  * device-generated ones (TNTT_OK = identical) */
 int tntt_rns_plan_check_tables(const tntt_rns_plan *plan, int limb);

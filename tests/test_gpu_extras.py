@@ -422,8 +422,17 @@ def test_rns_one_launch_matches_oracle_limb_by_limb(n, limbs, below):
         for l, (q, psi) in enumerate(zip(moduli, psis)):
             assert (got[l] == co.nwc_poly_mult(a[l], b[l], psi, q, threads=8)).all(), (l, q)
     # the single-modulus plans (host-built tables) give the same bits
+    c = ctx.polymul(da, db)
     single = torch.stack([tntt.polymul(pl, da[l], db[l]) for l, pl in enumerate(ctx.plans)])
-    assert torch.equal(single, ctx.polymul(da, db))
+    assert torch.equal(single, c)
+    # transform-domain entry points, every limb per launch: same spectra as the single-modulus plans, same products
+    sb = ctx.forward_spectrum(db)
+    assert torch.equal(sb, torch.stack([tntt.forward_spectrum(pl, db[l]) for l, pl in enumerate(ctx.plans)]))
+    assert torch.equal(ctx.inverse_spectrum(sb), db)
+    assert torch.equal(ctx.polymul_spectrum(da, sb), c)
+    assert torch.equal(ctx.inverse_spectrum(ctx.pointwise(ctx.forward_spectrum(da), sb)), c)
+    shared = ctx.polymul_spectrum(da, sb[:, :1].contiguous())
+    assert torch.equal(shared, ctx.polymul(da, db[:, :1].expand_as(db).contiguous()))
 
 
 def test_rns_context_rejects_what_it_cannot_run():

@@ -678,6 +678,7 @@ constexpr int kRnsMaxLimbs = 16;
 template <typename W> struct RnsLimb {
     PolymulTables<W> tb;
     Mod<W> mod;
+    const Tw<W> *untwist;   // [N] psi^-i N^-1 (tb.post carries the extra 2^BITS of the Montgomery pointwise product)
 };
 template <typename W> struct RnsLimbs { RnsLimb<W> limb[kRnsMaxLimbs]; };
 
@@ -816,6 +817,59 @@ polymul_spectrum_kernel(const typename C::W *a, const typename C::W *bspec, type
     }
     dit_all<C, RED, 2, false, C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod);
     row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+}
+
+// The transform-domain kernels over all limbs of a multi-modulus batch in one launch (limb = blockIdx.y, tables out of
+// the kernel parameters like polymul_rns_kernel): OP 0 = spectrum_forward (a -> c), 1 = spectrum_inverse (a -> c),
+// 2 = polymul_spectrum (a coefficients, b spectra [L][B or 1][N] with row stride b_stride, -> c).
+template <class C, int RED, int MINB, int OP>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+spectrum_rns_kernel(const typename C::W *a, const typename C::W *bspec, typename C::W *c, size_t batch, size_t b_stride,
+                    const __grid_constant__ RnsLimbs<typename C::W> limbs) {
+    using W = typename C::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *tile = reinterpret_cast<W *>(smem_raw);
+    const PolymulTables<W> &tb = limbs.limb[blockIdx.y].tb;
+    const Mod<W> &mod = limbs.limb[blockIdx.y].mod;
+    const int tid = threadIdx.x & (C::P - 1), pl = threadIdx.x >> C::LOGP;
+    const size_t poly = (size_t)blockIdx.x * C::PPC + pl;
+    const bool active = poly < batch;
+    const size_t off = (size_t)blockIdx.y * batch * C::N + (active ? poly * C::N : 0);
+    if constexpr (OP == 0) {
+        W x[1][C::R];
+        row_load<C>(x[0], a + off, tid, active);
+        forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) {
+            const W v = csub(shoup_mul(x[0][k], (W)1, mod.one_p, mod.nq), mod.q);   // any word -> [0, q)
+            if (active) st_stream(c + off + (k << C::LOGP) + tid, v);
+        }
+    } else if constexpr (OP == 1) {
+        const Tw<W> *post = limbs.limb[blockIdx.y].untwist;
+        W x[C::R];
+        row_load<C>(x, a + off, tid, active);
+        dit_all<C, RED, 1, false, C::PREFETCH>(x, tile, pl, tid, tb.inv, post, mod);
+        row_store_scaled<C, 1>(x, c + off, tid, active, post, Tw<W>{0, 0}, mod);
+    } else {
+        const size_t b_rows = b_stride ? batch : 1;
+        const W *brow = bspec + (size_t)blockIdx.y * b_rows * C::N + (active ? poly * b_stride : 0);
+        W x[1][C::R], fa[C::R];
+        row_load<C>(x[0], a + off, tid, active);
+        forward_all<C, 1, RED, false>(x, tile, pl, tid, tb, mod);
+#pragma unroll
+        for (int k = 0; k < C::R; ++k) fa[k] = pointwise_product<C, RED>(x[0][k], __ldg(brow + (k << C::LOGP) + tid), mod);
+        dit_all<C, RED, 2, false, C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod);
+        row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+    }
+}
+// rtl/ntt_pointwise_mult.v:17-42 with the reference's Barrett product, all limbs in one launch (grid.y = limb)
+template <typename W>
+__global__ void __launch_bounds__(256)
+pointwise_rns_kernel(const W *a, const W *b, W *c, size_t count_per_limb, const __grid_constant__ RnsLimbs<W> limbs) {
+    const Mod<W> &mod = limbs.limb[blockIdx.y].mod;
+    const size_t off = (size_t)blockIdx.y * count_per_limb;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count_per_limb; i += (size_t)gridDim.x * blockDim.x)
+        c[off + i] = barrett_mul(a[off + i], b[off + i], mod);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -37,6 +37,9 @@ struct RnsVariant {
     cudaError_t (*launch)(const void *a, const void *b, void *c, size_t batch, const void *limbs, int nlimbs, cudaStream_t st);
     cudaError_t (*prepare)();
     cudaError_t (*attributes)(cudaFuncAttributes *attr, int *blocks_per_sm);
+    // transform-domain kernels of the same shape: op 0 = forward spectrum, 1 = inverse spectrum, 2 = product with b spectra
+    cudaError_t (*spectrum)(int op, const void *a, const void *b, void *c, size_t batch, size_t b_stride, const void *limbs,
+                            int nlimbs, cudaStream_t st);
 };
 
 template <class C, int NA, int RED, int MINB, int STASH = 0> struct RnsInst {
@@ -50,8 +53,30 @@ template <class C, int NA, int RED, int MINB, int STASH = 0> struct RnsInst {
             *static_cast<const RnsLimbs<W> *>(limbs));
         return cudaGetLastError();
     }
+    // the transform-domain kernels hold one operand: one tile, the occupancy of the single-modulus spectrum kernels
+    // (the unpadded tile: its twiddle-group depth is the one tuned for one operand at 80 registers; the spectrum
+    // order depends on R and P only, so it is the order of the single-modulus plans of the same size)
+    using CS = Cfg<W, C::LOGN, C::LOGR, C::PPC, 0>;
+    static constexpr size_t SP_SMEM = (size_t)CS::TILE * sizeof(W);
+    static constexpr int SP_MINB = (sizeof(W) == 4 && C::LOGR == 5) ? 2 : (NA == 2 ? MINB + 1 : MINB);
+    static cudaError_t spectrum(int op, const void *a, const void *b, void *c, size_t batch, size_t b_stride, const void *limbs,
+                                int nlimbs, cudaStream_t st) {
+        if (batch == 0 || nlimbs == 0) return cudaSuccess;
+        const dim3 grid((unsigned)((batch + C::PPC - 1) / C::PPC), (unsigned)nlimbs);
+        const W *pa = static_cast<const W *>(a), *pb = static_cast<const W *>(b);
+        W *pc = static_cast<W *>(c);
+        const RnsLimbs<W> &L = *static_cast<const RnsLimbs<W> *>(limbs);
+        if (op == 0) spectrum_rns_kernel<CS, RED, SP_MINB, 0><<<grid, C::THREADS, SP_SMEM, st>>>(pa, pb, pc, batch, b_stride, L);
+        else if (op == 1) spectrum_rns_kernel<CS, RED, SP_MINB, 1><<<grid, C::THREADS, SP_SMEM, st>>>(pa, pb, pc, batch, b_stride, L);
+        else spectrum_rns_kernel<CS, RED, SP_MINB, 2><<<grid, C::THREADS, SP_SMEM, st>>>(pa, pb, pc, batch, b_stride, L);
+        return cudaGetLastError();
+    }
     static cudaError_t prepare() {
-        return cudaFuncSetAttribute(polymul_rns_kernel<C, NA, RED, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        cudaError_t e = cudaFuncSetAttribute(polymul_rns_kernel<C, NA, RED, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_rns_kernel<CS, RED, SP_MINB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_rns_kernel<CS, RED, SP_MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spectrum_rns_kernel<CS, RED, SP_MINB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
+        return e;
     }
     static cudaError_t attributes(cudaFuncAttributes *attr, int *blocks_per_sm) {
         cudaError_t e = cudaFuncGetAttributes(attr, polymul_rns_kernel<C, NA, RED, MINB, STASH>);
@@ -62,7 +87,8 @@ template <class C, int NA, int RED, int MINB, int STASH = 0> struct RnsInst {
 #define RNS_VARIANT(NAME, WT, LN, LR, PPC, PAD, NA, RED, MINB, ST)                                              \
     RnsVariant { NAME, (int)sizeof(WT), LN, LR, RED, &RnsInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST>::launch, \
                  &RnsInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST>::prepare,                                \
-                 &RnsInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST>::attributes }
+                 &RnsInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST>::attributes,                             \
+                 &RnsInst<Cfg<WT, LN, LR, PPC, PAD>, NA, RED, MINB, ST>::spectrum }
 
 const RnsVariant kRnsVariants[] = {
     RNS_VARIANT("rns_u64_n12_r4_p1_a2_red1_b2_pad", uint64_t, 12, 4, 1, 1, 2, 1, 2, 0),
@@ -165,6 +191,7 @@ template <typename W> void fill_group(tntt_rns_plan *p, std::vector<RnsLimbs<W>>
         L.tb.fwd_last = static_cast<const Tw<W> *>(g.fwd_last);
         L.tb.post = static_cast<const Tw<W> *>(g.post);
         L.tb.inv.pyr = static_cast<const Tw<W> *>(g.inv_pyr);
+        L.untwist = static_cast<const Tw<W> *>(g.post_untwist);
         L.mod = host::make_mod<W>(g.q, p->logn);
     }
 }
@@ -357,6 +384,67 @@ int tntt_rns_polymul(const tntt_rns_plan *p, const void *a, const void *b, void 
         const size_t off = limb_bytes * first;
         CUDA_TRY(p->var->launch(static_cast<const char *>(a) + off, static_cast<const char *>(b) + off,
                                 static_cast<char *>(c) + off, batch, limbs, count, (cudaStream_t)stream));
+    }
+    return TNTT_OK;
+}
+
+namespace {
+int rns_io_check(const tntt_rns_plan *p, const void *a, const void *b, const void *c) {
+    if (!p) return api_fail(TNTT_BAD_ARG, "plan is null");
+    if (!a || !b || !c) return api_fail(TNTT_BAD_ARG, "null data pointer");
+    if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) return api_fail(TNTT_BAD_ARG, "data pointers must be 16-byte aligned");
+    return TNTT_OK;
+}
+// op 0 / 1 / 2 of RnsVariant::spectrum, one launch per kRnsMaxLimbs limbs
+int rns_spectrum(const tntt_rns_plan *p, int op, const void *a, const void *b, void *c, size_t batch, size_t b_rows, void *stream) {
+    if (batch == 0) return p ? TNTT_OK : api_fail(TNTT_BAD_ARG, "plan is null");
+    int rc = rns_io_check(p, a, op == 2 ? b : a, c);
+    if (rc) return rc;
+    if (op == 2 && b_rows != 1 && b_rows != batch) return api_fail(TNTT_BAD_ARG, "b_rows must be 1 (one spectrum per limb) or the batch size");
+    DevGuard dg(p->device);
+    const size_t row_bytes = (size_t)p->n * p->word_bytes;
+    const int ngroups = (p->limbs + kRnsMaxLimbs - 1) / kRnsMaxLimbs;
+    for (int g = 0; g < ngroups; ++g) {
+        const int first = g * kRnsMaxLimbs, count = p->limbs - first < kRnsMaxLimbs ? p->limbs - first : kRnsMaxLimbs;
+        const void *limbs = p->word_bytes == 4 ? (const void *)&p->groups32[g] : (const void *)&p->groups64[g];
+        const size_t off = row_bytes * batch * first, boff = op == 2 ? row_bytes * b_rows * first : 0;
+        CUDA_TRY(p->var->spectrum(op, static_cast<const char *>(a) + off, b ? static_cast<const char *>(b) + boff : nullptr,
+                                  static_cast<char *>(c) + off, batch, (op == 2 && b_rows == batch) ? p->n : 0, limbs, count,
+                                  (cudaStream_t)stream));
+    }
+    return TNTT_OK;
+}
+}  // namespace
+
+int tntt_rns_spectrum_forward(const tntt_rns_plan *p, const void *in, void *out, size_t batch, void *stream) {
+    return rns_spectrum(p, 0, in, nullptr, out, batch, 0, stream);
+}
+int tntt_rns_spectrum_inverse(const tntt_rns_plan *p, const void *in, void *out, size_t batch, void *stream) {
+    return rns_spectrum(p, 1, in, nullptr, out, batch, 0, stream);
+}
+int tntt_rns_polymul_spectrum(const tntt_rns_plan *p, const void *a, const void *b_spectrum, void *c, size_t batch, size_t b_rows,
+                              void *stream) {
+    return rns_spectrum(p, 2, a, b_spectrum, c, batch, b_rows, stream);
+}
+int tntt_rns_pointwise(const tntt_rns_plan *p, const void *a, const void *b, void *c, size_t batch, void *stream) {
+    if (batch == 0) return p ? TNTT_OK : api_fail(TNTT_BAD_ARG, "plan is null");
+    int rc = rns_io_check(p, a, b, c);
+    if (rc) return rc;
+    DevGuard dg(p->device);
+    const size_t count = batch * p->n, row_bytes = (size_t)p->n * p->word_bytes;
+    const int ngroups = (p->limbs + kRnsMaxLimbs - 1) / kRnsMaxLimbs;
+    for (int g = 0; g < ngroups; ++g) {
+        const int first = g * kRnsMaxLimbs, nl = p->limbs - first < kRnsMaxLimbs ? p->limbs - first : kRnsMaxLimbs;
+        const size_t off = row_bytes * batch * first;
+        const size_t want = (count + 255) / 256;
+        const dim3 grid((unsigned)(want < 148u * 16u ? (want ? want : 1) : 148u * 16u), (unsigned)nl);
+        if (p->word_bytes == 4)
+            pointwise_rns_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                (const uint32_t *)((const char *)a + off), (const uint32_t *)((const char *)b + off), (uint32_t *)((char *)c + off), count, p->groups32[g]);
+        else
+            pointwise_rns_kernel<uint64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                (const uint64_t *)((const char *)a + off), (const uint64_t *)((const char *)b + off), (uint64_t *)((char *)c + off), count, p->groups64[g]);
+        CUDA_TRY(cudaGetLastError());
     }
     return TNTT_OK;
 }

@@ -24,6 +24,7 @@ SYMBOLS = (
     "tntt_rns_plan_create", "tntt_rns_plan_destroy", "tntt_rns_plan_limbs", "tntt_rns_plan_word_bytes",
     "tntt_rns_plan_kernel", "tntt_rns_plan_table_bytes", "tntt_rns_polymul", "tntt_rns_plan_check_tables",
     "tntt_rns_kernel_attributes", "tntt_find_psi", "tntt_polymul_host_multi",
+    "tntt_rns_spectrum_forward", "tntt_rns_spectrum_inverse", "tntt_rns_polymul_spectrum", "tntt_rns_pointwise",
 )
 
 
@@ -94,6 +95,9 @@ def lib() -> C.CDLL:
     L.tntt_rns_plan_table_bytes.restype = sz
     L.tntt_rns_polymul.argtypes = [vp, vp, vp, vp, sz, vp]
     L.tntt_rns_plan_check_tables.argtypes = [vp, i]
+    L.tntt_rns_spectrum_forward.argtypes = L.tntt_rns_spectrum_inverse.argtypes = [vp, vp, vp, sz, vp]
+    L.tntt_rns_polymul_spectrum.argtypes = [vp, vp, vp, vp, sz, sz, vp]
+    L.tntt_rns_pointwise.argtypes = [vp, vp, vp, vp, sz, vp]
     L.tntt_rns_kernel_attributes.argtypes = [vp, C.POINTER(i), C.POINTER(sz), C.POINTER(i)]
     L.tntt_find_psi.argtypes = [u32, u64, u64, C.POINTER(u64)]
     L.tntt_last_error.restype = C.c_char_p

@@ -136,34 +136,53 @@ class RnsContext:
             ops.inverse(plan, ta[l], twist=twist, out=o[l])
         return o
 
-    # ---- operands kept in the transform domain (one spectrum per limb; see ops.forward_spectrum) ----
-    def _per_limb(self, fn, a, out, *rest):
+    # ---- operands kept in the transform domain: [L, B, N] spectra, every limb in one launch (csrc/rns.cu) ----
+    def _stream(self):
         import torch
 
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _unary(self, fn, a, out):
         ta = ops.as_tensor(a)
         self._check(ta, "a")
-        o = torch.empty_like(ta) if out is None else out
-        for l, plan in enumerate(self.plans):
-            fn(plan, ta[l], *[r[l] for r in rest], out=o[l])
+        ta = ta.contiguous()
+        o = ops._out_like(ta, out)
+        check(fn(self._h, ta.data_ptr(), o.data_ptr(), ta.shape[1], self._stream()))
         return o
 
     def forward_spectrum(self, a, out=None):
-        return self._per_limb(ops.forward_spectrum, a, out)
+        """Coefficients -> spectra (tntt_rns_spectrum_forward): ntt(twist(.)) of every row of every limb, canonical, in the
+        spectrum order of the single-modulus plans of the same size."""
+        return self._unary(lib().tntt_rns_spectrum_forward, a, out)
 
     def inverse_spectrum(self, a, out=None):
-        return self._per_limb(ops.inverse_spectrum, a, out)
+        """Spectra -> coefficients (tntt_rns_spectrum_inverse)."""
+        return self._unary(lib().tntt_rns_spectrum_inverse, a, out)
 
     def pointwise(self, a, b, out=None):
-        tb = ops.as_tensor(b)
+        """Element-wise product mod q_l of two [L, B, N] tensors (spectra or not): tntt_rns_pointwise."""
+        ta, tb = ops.as_tensor(a), ops.as_tensor(b)
+        self._check(ta, "a")
         self._check(tb, "b")
-        return self._per_limb(ops.pointwise, a, out, tb)
+        if ta.shape != tb.shape or ta.dtype != tb.dtype:
+            raise ValueError("a and b must have the same shape and dtype")
+        ta, tb = ta.contiguous(), tb.contiguous()
+        o = ops._out_like(ta, out)
+        check(lib().tntt_rns_pointwise(self._h, ta.data_ptr(), tb.data_ptr(), o.data_ptr(), ta.shape[1], self._stream()))
+        return o
 
     def polymul_spectrum(self, a, b_spectrum, out=None):
         """out[l] = a[l] * b[l] with b given as per-limb spectra, shape [L, B, N] or [L, 1, N] (shared by the batch)."""
-        tb = ops.as_tensor(b_spectrum)
-        if tb.dim() != 3 or tb.shape[0] != len(self.moduli) or tb.shape[-1] != self.n:
-            raise ValueError(f"b_spectrum must have shape [L={len(self.moduli)}, B or 1, N={self.n}]")
-        return self._per_limb(ops.polymul_spectrum, a, out, tb)
+        ta, tb = ops.as_tensor(a), ops.as_tensor(b_spectrum)
+        self._check(ta, "a")
+        self._check(tb, "b_spectrum")
+        if tb.dtype != ta.dtype or tb.shape[1] not in (1, ta.shape[1]):
+            raise ValueError(f"b_spectrum must have shape [L={len(self.moduli)}, B or 1, N={self.n}] and a's dtype")
+        ta, tb = ta.contiguous(), tb.contiguous()
+        o = ops._out_like(ta, out)
+        check(lib().tntt_rns_polymul_spectrum(self._h, ta.data_ptr(), tb.data_ptr(), o.data_ptr(), ta.shape[1], tb.shape[1],
+                                              self._stream()))
+        return o
 
     # ---- host-side helpers (tests, small data) ------------------------------------------------
     def decompose(self, coeffs: Sequence[Sequence[int]]):
