@@ -100,7 +100,7 @@ template <class C, int NA, int RED> struct Emu {
             dit_from<pointwise_out_bound<C, RED>(), 0>(tb.inv);
             for (int t = 0; t < T; ++t) {
                 size_t o = off(t, act);
-                row_store_scaled<C>(F(t), c + o, t & (C::P - 1), act, tb.post, Tw<W>{0, 0}, mod);
+                row_store_scaled<C, 1, C::POST_GROUP, RED>(F(t), c + o, t & (C::P - 1), act, tb.post, Tw<W>{0, 0}, mod);
             }
         }
     }
@@ -142,7 +142,7 @@ template <class C, int NA, int RED> struct Emu {
             dit_from<1, 0>(tb.inv);
             for (int t = 0; t < T; ++t) {
                 const size_t poly = cta * C::PPC + (t >> C::LOGP);
-                if (post) row_store_scaled<C, 1>(F(t), out + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, post, Tw<W>{0, 0}, mod);
+                if (post) row_store_scaled<C, 1, C::POST_GROUP, RED>(F(t), out + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, post, Tw<W>{0, 0}, mod);
                 else row_store_scaled<C, 0>(F(t), out + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, nullptr, uniform, mod);
             }
         }
@@ -168,7 +168,7 @@ template <class C, int NA, int RED> struct Emu {
             dit_from<2, 0>(tb.inv);
             for (int t = 0; t < T; ++t) {
                 const size_t poly = cta * C::PPC + (t >> C::LOGP);
-                row_store_scaled<C, 1>(F(t), c + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, tb.post, Tw<W>{0, 0}, mod);
+                row_store_scaled<C, 1, C::POST_GROUP, RED>(F(t), c + (poly < batch ? poly * C::N : 0), t & (C::P - 1), poly < batch, tb.post, Tw<W>{0, 0}, mod);
             }
         }
     }

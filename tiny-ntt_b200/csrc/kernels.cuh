@@ -459,13 +459,36 @@ template <class C> TNTT_HD void row_load(typename C::W (&x)[C::R], const typenam
 // final multiply (psi^-i N^-1 ...) + canonical reduction + coalesced store.
 // TABLE: 1 = per-coefficient table `post` (loaded GROUP entries at a time so that their L2 latencies
 // overlap instead of one exposed load per coefficient), 0 = one uniform factor, -1 = decided at run time.
-template <class C, int TABLE = -1, int GROUP_ = C::POST_GROUP>
+// RED = 2 (q = 2^60 - 2^14 + 1): the product is solinas_mul() -- 4 wide multiplies and ALU folds instead of the exact
+// Shoup product's 6 wide + 4 narrow, on a kernel whose multiplier pipe is the binding unit; only the table's w is read.
+#ifndef TNTT_SOLINAS_STORE
+#define TNTT_SOLINAS_STORE 1
+#endif
+template <class C, int TABLE = -1, int GROUP_ = C::POST_GROUP, int RED = 0>
 TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row, int tid, bool active,
                               const Tw<typename C::W> *post, const Tw<typename C::W> &post_uniform,
                               const Mod<typename C::W> &mod) {
     using W = typename C::W;
     constexpr int GROUP = GROUP_ < C::R ? GROUP_ : C::R;
-    if (TABLE == 1 || (TABLE == -1 && post)) {
+    if constexpr (RED == 2 && TABLE == 1 && TNTT_SOLINAS_STORE) {
+#pragma unroll
+        for (int k0 = 0; k0 < C::R; k0 += GROUP) {
+            W w[GROUP];
+#pragma unroll
+            for (int j = 0; j < GROUP; ++j) {
+#if defined(__CUDA_ARCH__)
+                w[j] = __ldg(&post[((k0 + j) << C::LOGP) + tid].w);
+#else
+                w[j] = post[((k0 + j) << C::LOGP) + tid].w;
+#endif
+            }
+#pragma unroll
+            for (int j = 0; j < GROUP; ++j) {
+                const W v = csub(solinas_mul(x[k0 + j], w[j]), mod.q);    // below 2^60 + 2^37 < 2 q: one subtraction
+                if (active) st_stream(row + ((k0 + j) << C::LOGP) + tid, v);
+            }
+        }
+    } else if (TABLE == 1 || (TABLE == -1 && post)) {
 #pragma unroll
         for (int k0 = 0; k0 < C::R; k0 += GROUP) {
             Tw<W> t[GROUP];
@@ -787,7 +810,7 @@ spectrum_inverse_kernel(const typename C::W *in, typename C::W *out, size_t batc
         for (int k = 0; k < C::R; ++k) x[k] = tile[C::spos(pl * C::N + ((cbitrev(k, C::LOGR) << C::LOGP) | bt))];
     }
     dit_all<C, RED, 1, false, C::PREFETCH>(x, tile, pl, tid, inv, TABLE ? post : nullptr, mod);   // canonical input: below one unit
-    row_store_scaled<C, TABLE ? 1 : 0>(x, out + off, tid, active, post, post_uniform, mod);
+    row_store_scaled<C, TABLE ? 1 : 0, C::POST_GROUP, RED>(x, out + off, tid, active, post, post_uniform, mod);
 }
 
 // b_stride = N: one spectrum per row; b_stride = 0: one spectrum shared by the whole batch
@@ -816,7 +839,7 @@ polymul_spectrum_kernel(const typename C::W *a, const typename C::W *bspec, type
         fa[k] = pointwise_product<C, RED>(x[0][k], __ldg(brow + (k << C::LOGP) + tid), mod);   // red 1: < u*q/2^BITS + q, below two units
     }
     dit_all<C, RED, 2, false, C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod);
-    row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+    row_store_scaled<C, 1, C::POST_GROUP, RED>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
 }
 
 // The transform-domain kernels over all limbs of a multi-modulus batch in one launch (limb = blockIdx.y, tables out of
@@ -849,7 +872,7 @@ spectrum_rns_kernel(const typename C::W *a, const typename C::W *bspec, typename
         W x[C::R];
         row_load<C>(x, a + off, tid, active);
         dit_all<C, RED, 1, false, C::PREFETCH>(x, tile, pl, tid, tb.inv, post, mod);
-        row_store_scaled<C, 1>(x, c + off, tid, active, post, Tw<W>{0, 0}, mod);
+        row_store_scaled<C, 1, C::POST_GROUP, RED>(x, c + off, tid, active, post, Tw<W>{0, 0}, mod);
     } else {
         const size_t b_rows = b_stride ? batch : 1;
         const W *brow = bspec + (size_t)blockIdx.y * b_rows * C::N + (active ? poly * b_stride : 0);
@@ -859,7 +882,7 @@ spectrum_rns_kernel(const typename C::W *a, const typename C::W *bspec, typename
 #pragma unroll
         for (int k = 0; k < C::R; ++k) fa[k] = pointwise_product<C, RED>(x[0][k], __ldg(brow + (k << C::LOGP) + tid), mod);
         dit_all<C, RED, 2, false, C::PREFETCH>(fa, tile, pl, tid, tb.inv, tb.post, mod);
-        row_store_scaled<C, 1>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
+        row_store_scaled<C, 1, C::POST_GROUP, RED>(fa, c + off, tid, active, tb.post, Tw<W>{0, 0}, mod);
     }
 }
 // rtl/ntt_pointwise_mult.v:17-42 with the reference's Barrett product, all limbs in one launch (grid.y = limb)
