@@ -457,3 +457,33 @@ def test_rns_context_rejects_what_it_cannot_run():
     with pytest.raises(ValueError):
         ctx.polymul(a.cpu(), a.cpu())
     assert ctx.polymul(a[:, :0], a[:, :0]).shape == (2, 0, 4096)
+
+
+def test_polymul_sharded_over_all_visible_gpus():
+    """tntt_polymul_host_multi: one process, one plan per device, contiguous row ranges (ragged on purpose), host barrier.
+    On a one-GPU box this is the single-plan path; with more devices visible every GPU takes its share."""
+    import tntt
+
+    p = O.PARAMS["n4096_60"]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    plans = tntt.get_plans(n, q, psi)
+    assert len(plans) == torch.cuda.device_count() and len({pl.device for pl in plans}) == len(plans)
+    rng = np.random.default_rng(len(plans))
+    rows = 37 * len(plans) + 5
+    a = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(rows, n), dtype=np.uint64)
+    ha, hb = torch.from_numpy(a.view(np.int64)).pin_memory(), torch.from_numpy(b.view(np.int64)).pin_memory()
+    hc = tntt.polymul_sharded(plans, ha, hb)
+    assert (hc.numpy().view(np.uint64) == COracle().nwc_poly_mult(a, b, psi, q, threads=8)).all()
+    out = torch.empty_like(ha)
+    assert tntt.polymul_sharded(plans, ha[:3], hb[:3], out=out[:3]) is not None       # fewer rows than devices is fine
+    assert torch.equal(out[:3], hc[:3])
+    with pytest.raises(tntt.TnttError):
+        tntt.polymul_sharded([plans[0], plans[0]], ha, hb)                             # one plan per device
+    with pytest.raises(ValueError):
+        tntt.polymul_sharded(plans, ha.cuda(), hb.cuda())
+    with pytest.raises(ValueError):
+        tntt.polymul_sharded(plans, ha, hb, out=torch.empty((1, n), dtype=torch.int64))
+    other = tntt.get_plan(256, 8380417, 1239911, True)
+    with pytest.raises((tntt.TnttError, ValueError, TypeError)):
+        tntt.polymul_sharded([other], ha, hb)

@@ -459,36 +459,16 @@ template <class C> TNTT_HD void row_load(typename C::W (&x)[C::R], const typenam
 // final multiply (psi^-i N^-1 ...) + canonical reduction + coalesced store.
 // TABLE: 1 = per-coefficient table `post` (loaded GROUP entries at a time so that their L2 latencies
 // overlap instead of one exposed load per coefficient), 0 = one uniform factor, -1 = decided at run time.
-// RED = 2 (q = 2^60 - 2^14 + 1): the product is solinas_mul() -- 4 wide multiplies and ALU folds instead of the exact
-// Shoup product's 6 wide + 4 narrow, on a kernel whose multiplier pipe is the binding unit; only the table's w is read.
-#ifndef TNTT_SOLINAS_STORE
-#define TNTT_SOLINAS_STORE 1
-#endif
+// (RED is accepted for symmetry with the other building blocks.  A Solinas form of this product for RED 2 -- four wide
+// multiplies and ALU folds instead of the exact Shoup product's six wide + four narrow -- was measured SLOWER on B200,
+// 13.05 vs 13.54 M polymul/s, profiles/r02_whatif_store.log: at the tail of the kernel nothing overlaps the ALU folds.)
 template <class C, int TABLE = -1, int GROUP_ = C::POST_GROUP, int RED = 0>
 TNTT_HD void row_store_scaled(const typename C::W (&x)[C::R], typename C::W *row, int tid, bool active,
                               const Tw<typename C::W> *post, const Tw<typename C::W> &post_uniform,
                               const Mod<typename C::W> &mod) {
     using W = typename C::W;
     constexpr int GROUP = GROUP_ < C::R ? GROUP_ : C::R;
-    if constexpr (RED == 2 && TABLE == 1 && TNTT_SOLINAS_STORE) {
-#pragma unroll
-        for (int k0 = 0; k0 < C::R; k0 += GROUP) {
-            W w[GROUP];
-#pragma unroll
-            for (int j = 0; j < GROUP; ++j) {
-#if defined(__CUDA_ARCH__)
-                w[j] = __ldg(&post[((k0 + j) << C::LOGP) + tid].w);
-#else
-                w[j] = post[((k0 + j) << C::LOGP) + tid].w;
-#endif
-            }
-#pragma unroll
-            for (int j = 0; j < GROUP; ++j) {
-                const W v = csub(solinas_mul(x[k0 + j], w[j]), mod.q);    // below 2^60 + 2^37 < 2 q: one subtraction
-                if (active) st_stream(row + ((k0 + j) << C::LOGP) + tid, v);
-            }
-        }
-    } else if (TABLE == 1 || (TABLE == -1 && post)) {
+    if (TABLE == 1 || (TABLE == -1 && post)) {
 #pragma unroll
         for (int k0 = 0; k0 < C::R; k0 += GROUP) {
             Tw<W> t[GROUP];
@@ -808,6 +788,9 @@ spectrum_inverse_kernel(const typename C::W *in, typename C::W *out, size_t batc
         tile_sync<C>();
 #pragma unroll
         for (int k = 0; k < C::R; ++k) x[k] = tile[C::spos(pl * C::N + ((cbitrev(k, C::LOGR) << C::LOGP) | bt))];
+        // this permuted read touches the whole tile, while the first regrouping of dit_all() is ordered by a warp
+        // barrier only (exchange_is_warp_local): everybody must be done reading before any warp writes again
+        tile_sync<C>();
     }
     dit_all<C, RED, 1, false, C::PREFETCH>(x, tile, pl, tid, inv, TABLE ? post : nullptr, mod);   // canonical input: below one unit
     row_store_scaled<C, TABLE ? 1 : 0, C::POST_GROUP, RED>(x, out + off, tid, active, post, post_uniform, mod);
