@@ -512,6 +512,7 @@ def run_ours(args):
             val = tot * reps / (o_ms * 1e-3)
             per_gpu = val / world if batch_total is None else val * nrows_gpu / max(tot, 1)
             rec = {"tag": otag, "n": op["n"], "q": op["q"], "rows_per_gpu": nrows_gpu, "rows_total": tot, "value": val,
+                   "value_per_gpu": per_gpu,
                    "unit": UNIT, "us_per_launch": o_ms * 1e3 / reps, "launches": reps,
                    "hbm_frac": per_gpu * 3 * op["n"] * pl.word_bytes / 1e9 / peaks["hbm_gbs"],
                    "kernel_variant": dict(pl.variants()).get(pl.default_variant, "?").split(" ")[0]}
@@ -569,6 +570,10 @@ def run_ours(args):
     else:
         roofline = dict(roofline_hbm, kernel=variant_name,
                         note="no executed-instruction histogram committed for this variant (tools/sass_slots.py): HBM roofline only")
+    for rec in others or []:      # the same ceiling for the other configurations' kernels
+        sl = load_json("sass_slots.json").get(rec["tag"])
+        if sl and sl.get("variant") == rec["kernel_variant"]:
+            rec["mul_pipe_frac"] = rec["value_per_gpu"] * sl["warps_per_row"] * sl["pipe_cycles_per_warp"] / (sms * 4 * sm_mhz * 1e6)
     # SURVEY section 8(d)'s accounting beside it: IMAD32 per polymul x polymul/s against the IMAD.LO rate measured in this run
     roofline_imad32 = None
     try:

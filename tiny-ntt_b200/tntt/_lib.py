@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libtntt.so")
+# TNTT_LIB_PATH: load another build of the same sources (e.g. the -DTNTT_DEBUG_BOUNDS one, csrc/Makefile `debug`)
+LIB_PATH = os.environ.get("TNTT_LIB_PATH") or os.path.join(PKG_DIR, "libtntt.so")
 
 TNTT_OK = 0
 TNTT_BAD_ARG, TNTT_BAD_ROOT, TNTT_UNSUPPORTED_N, TNTT_CUDA_ERROR = -1, -2, -3, -4

@@ -74,7 +74,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("report")
     ap.add_argument("--kernel", default=None, help="regex on the kernel name (default: first kernel in the report)")
-    ap.add_argument("--warps-per-row", type=int, default=8)
+    ap.add_argument("--warps-per-row", type=float, default=8, help="warps that share one polynomial pair (N=256: 16 lanes = 0.5)")
     ap.add_argument("--sms", type=int, default=148)
     ap.add_argument("--clock-mhz", type=float, default=1965.0)
     ap.add_argument("--tag", default=None)
