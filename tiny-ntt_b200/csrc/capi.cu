@@ -313,6 +313,12 @@ int create_plan(tntt_plan **out, int device, uint32_t n, uint64_t q, uint64_t ro
         }
     I.default_variant = choose_default_variant(p);
     I.fused = I.default_variant >= 0 ? 1 : 0;
+    // rows on thread-block clusters (N = 16384, 32768): the transform-domain kernels have the cluster shape of the fused
+    // kernel, which choose_default_variant() only accepts when the device can co-schedule it (cudaOccupancyMaxActiveClusters)
+    if (p->spectrum && p->spectrum->cluster && !(I.default_variant >= 0 && vs[I.default_variant].cluster)) {
+        p->spectrum = nullptr;
+        I.spectrum = 0;
+    }
     choose_small_batch_variants(p);
     CUDA_TRY(cudaDeviceSynchronize());
     *out = p;
@@ -332,6 +338,11 @@ int generic_transform(const tntt_plan *p, const void *in, void *out, size_t batc
     const int wb = p->info.word_bytes, logn = (int)p->info.logn;
     const size_t bytes = batch * p->info.n * (size_t)wb;
     void *s0 = nullptr, *s1 = nullptr;
+    struct Scratch {   // released on every path out of this function, error returns included
+        void *&a, *&b;
+        cudaStream_t st;
+        ~Scratch() { if (a) cudaFreeAsync(a, st); if (b) cudaFreeAsync(b, st); }
+    } scratch{s0, s1, st};
     CUDA_TRY(cudaMallocAsync(&s0, bytes, st));
     CUDA_TRY(cudaMallocAsync(&s1, bytes, st));
     const void *src = in;
@@ -346,8 +357,6 @@ int generic_transform(const tntt_plan *p, const void *in, void *out, size_t batc
     if (inverse && (flags & TNTT_TWIST)) CUDA_TRY(launch_mul_table(wb, cur, out, batch, logn, p->post_untwist, p->mod(), st));
     else if (inverse) CUDA_TRY(launch_scale(wb, cur, out, batch * p->info.n, p->ninv_tw.w, wb == 4 ? host::make_tw<uint32_t>(p->info.n_inv, p->info.q).wp : p->ninv_tw.wp, p->mod(), st));
     else CUDA_TRY(cudaMemcpyAsync(out, cur, bytes, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaFreeAsync(s0, st));
-    CUDA_TRY(cudaFreeAsync(s1, st));
     return TNTT_OK;
 }
 

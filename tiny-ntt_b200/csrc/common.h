@@ -45,6 +45,7 @@ struct SpectrumVariant {
     cudaError_t (*forward_natural)(const void *in, void *out, size_t batch, const void *tables, const void *mod, cudaStream_t st);
     cudaError_t (*inverse_natural)(const void *in, void *out, size_t batch, const void *tables, const void *post, uint64_t uw,
                                    uint64_t uwp, const void *mod, cudaStream_t st);   // post == nullptr: scale by {uw, uwp}
+    int cluster = 0;   // > 0: one row per thread-block cluster of this many CTAs
 };
 const SpectrumVariant *spectrum_variants(int *count);
 

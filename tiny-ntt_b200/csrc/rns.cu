@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -98,6 +99,8 @@ const RnsVariant kRnsVariants[] = {
     RNS_VARIANT("rns_u64_n8_r4_p16_a1_red1_b2", uint64_t, 8, 4, 16, 0, 1, 1, 2, 0),
     RNS_VARIANT("rns_u64_n8_r4_p16_a1_red0_b2", uint64_t, 8, 4, 16, 0, 1, 0, 2, 0),
     RNS_VARIANT("rns_u32_n12_r4_p1_a2_red0_b3", uint32_t, 12, 4, 1, 0, 2, 0, 3, 0),
+    RNS_VARIANT("rns_u32_n12_r4_p1_a2_red0_b2", uint32_t, 12, 4, 1, 0, 2, 0, 2, 0),     // alternatives: TNTT_RNS_PICK=1, 2 (tools/rns_bench.py)
+    RNS_VARIANT("rns_u32_n12_r4_p1_a1_red0_b4", uint32_t, 12, 4, 1, 0, 1, 0, 4, 0),
     RNS_VARIANT("rns_u32_n10_r5_p8_a2_red0_b2", uint32_t, 10, 5, 8, 0, 2, 0, 2, 0),
     RNS_VARIANT("rns_u32_n8_r4_p16_a2_red0_b3", uint32_t, 8, 4, 16, 0, 2, 0, 3, 0),
 };
@@ -287,8 +290,13 @@ int tntt_rns_plan_create(tntt_rns_plan **out, int device, uint32_t n, const uint
         else if (r > red) red = r;      // the lazily reducing kernels serve every modulus of their word size
     }
     const RnsVariant *var = nullptr;
+    int pick = 0;   // the first matching shape is the measured default; TNTT_RNS_PICK=k selects the k-th match (benchmarking)
+    if (const char *env = getenv("TNTT_RNS_PICK")) pick = atoi(env);
     for (const RnsVariant &v : kRnsVariants)
-        if (v.word_bytes == word && v.logn == logn && v.red == red) { var = &v; break; }
+        if (v.word_bytes == word && v.logn == logn && v.red == red) {
+            var = &v;
+            if (pick-- <= 0) break;
+        }
     if (!var) return api_fail(TNTT_UNSUPPORTED_N, "no multi-modulus kernel for n=%u with %d-byte words (n in {256, 1024, 4096})", n, word);
 
     DevGuard dg(device);

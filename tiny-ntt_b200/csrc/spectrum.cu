@@ -106,7 +106,7 @@ template <class C, int CS, int RED, int MINB> struct SpectrumClusterInst {
             &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::forward,                           \
             &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::inverse,                           \
             &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::polymul,                           \
-            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::prepare, nullptr, nullptr          \
+            &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::prepare, nullptr, nullptr, CS      \
     }
 
 #define TNTT_SPECTRUM_VARIANT(WT, WB, LN, LR, PPC, RED, MINB)                                                \
