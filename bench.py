@@ -335,9 +335,11 @@ def run_ours(args):
     tag = args.config
     p = PARAMS[tag]
     n, q, psi = p["n"], p["q"], p["psi"]
-    plan = tntt.get_plan(n, q, psi, True, local)
-    if args.variant >= 0:
+    if args.variant >= 0:      # a private, uncached plan: set_default_variant rewrites the plan's dispatch fields
+        plan = tntt.Plan.create(n, q, psi, True, local)
         plan.set_default_variant(args.variant)
+    else:
+        plan = tntt.get_plan(n, q, psi, True, local)
     variant_desc = dict(plan.variants()).get(plan.default_variant, "literal-schedule path")
     variant_name = variant_desc.split(" ")[0]
     rows = args.rows or ROWS[tag]

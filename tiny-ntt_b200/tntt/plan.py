@@ -80,8 +80,15 @@ class Plan:
         return out
 
     def set_default_variant(self, variant: int) -> None:
+        """Benchmarking knob (tntt_plan_set_default_variant): rewrites this plan's dispatch fields and switches the
+        batch-size dispatch off.  Not thread-safe, and a plan from get_plan() is shared by every caller of the same ring:
+        use it on a private plan (Plan.create) only."""
         check(lib().tntt_plan_set_default_variant(self._h, variant))
-        self.default_variant = variant
+        info = PlanInfo()
+        check(lib().tntt_plan_info_get(self._h, C.byref(info)))
+        self.info = info
+        for name, _ in PlanInfo._fields_:
+            setattr(self, name, getattr(info, name))
 
     @property
     def torch_dtypes(self):
