@@ -43,7 +43,7 @@ def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rnd = random.Random(2026)
     co = COracle()
-    t0, cases = time.time(), 0
+    t0, cases, bigs = time.time(), 0, 0
     while time.time() - t0 < budget:
         logn = rnd.choice([8, 9, 10, 11, 12, 13, 14, 15])
         n = 1 << logn
@@ -80,8 +80,31 @@ def main():
         omega = psi * psi % q
         assert (host(tntt.forward(plan, ta)) == co.cg_ntt(a, omega, q)).all(), ("cg_ntt", n, q, rows)
         assert (host(tntt.inverse(plan, ta)) == co.cg_intt(a, omega, q)).all(), ("cg_intt", n, q, rows)
+        # twisted natural-order transforms (the permuted tile paths) against the fused product
+        if plan.spectrum:
+            fa, fb = tntt.forward(plan, ta, twist=True), tntt.forward(plan, tb, twist=True)
+            assert (host(tntt.inverse(plan, tntt.pointwise(plan, fa, fb), twist=True)) == want).all(), ("twisted", n, q, rows)
+        # every few cases: a batch that fills the GPU several times over (ordering bugs between warps / CTAs only show
+        # under load), checked by identities between independent kernel paths instead of the CPU oracle
+        if cases % 4 == 0 and logn <= 13:
+            big = max(2048, (1 << 24) >> logn)
+            g = torch.Generator(device="cuda").manual_seed(cases)
+            xa = torch.randint(0, q, (big, n), generator=g, device="cuda", dtype=torch.int64).to(plan.dtype)
+            xb = torch.randint(0, q, (big, n), generator=g, device="cuda", dtype=torch.int64).to(plan.dtype)
+            c0 = tntt.polymul(plan, xa, xb)
+            for v, d in plan.variants():
+                assert torch.equal(tntt.polymul(plan, xa, xb, variant=v), c0), ("big batch, variant", d, n, q)
+            assert torch.equal(tntt.inverse(plan, tntt.forward(plan, xa)), xa), ("big batch, round trip", n, q)
+            if plan.spectrum:
+                sb = tntt.forward_spectrum(plan, xb)
+                assert torch.equal(tntt.polymul_spectrum(plan, xa, sb), c0), ("big batch, spectrum", n, q)
+                assert torch.equal(tntt.inverse_spectrum(plan, sb), xb), ("big batch, spectrum round trip", n, q)
+                fa, fb = tntt.forward(plan, xa, twist=True), tntt.forward(plan, xb, twist=True)
+                assert torch.equal(tntt.inverse(plan, tntt.pointwise(plan, fa, fb), twist=True), c0), ("big batch, twisted", n, q)
+            del xa, xb, c0
+            bigs += 1
         cases += 1
-    print(f"stress ok: {cases} random (n, q, batch) cases in {time.time() - t0:.0f} s")
+    print(f"stress ok: {cases} random (n, q, batch) cases ({bigs} with GPU-filling batches) in {time.time() - t0:.0f} s")
 
 
 if __name__ == "__main__":
