@@ -200,3 +200,33 @@ def test_find_psi_matches_the_reference_script():
     assert L.tntt_find_psi(256, 7687, 10000, C.byref(psi)) < 0          # prime, but not 1 mod 512
     with pytest.raises(ValueError):
         tntt.find_psi(4096, 12289)
+
+
+def test_bench_contract_of_the_reference_arm_and_shared_config():
+    """bench.py --impl reference (CPU only) prints ONE JSON line with the contract's keys, and its `config` object is the
+    one the GPU arm builds for the same workload (the driver compares the two)."""
+    import json
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--config", "dilithium"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["sample_rows"] > 0
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.workload_config("dilithium", bench.ROWS["dilithium"], 1)
+    assert set(d["config"]) == {"workload", "n", "q", "psi", "rows_per_gpu", "rows_total", "gpus", "l2"}
+    # the sweep of BASELINE config 5 splits its TOTAL batch into contiguous shares, ranks beyond the batch idle
+    for world in (1, 2, 4, 8):
+        for B in bench.SWEEP_BATCHES:
+            per = (B + world - 1) // world
+            shares = [max(0, min(per, B - r * per)) for r in range(world)]
+            assert sum(shares) == B and all(s >= 0 for s in shares)
