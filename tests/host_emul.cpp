@@ -341,6 +341,9 @@ int emu_spectrum(int word_bytes, int logn, int logr, int ppc, int red, const voi
 // red: 0 / 1 / 2 (Solinas, q = 2^60 - 2^14 + 1 only); pad: 1 = padded tile
 int emu_polymul_ex(int word_bytes, int logn, int logr, int ppc, int na, int red, int pad, const void *a, const void *b, void *c,
                    size_t batch, uint64_t q, uint64_t psi) {
+    POLY_CASE_P(4, uint32_t, 8, 4, 16, 2, 0, 1)
+    POLY_CASE_P(4, uint32_t, 10, 5, 8, 2, 0, 1)
+    POLY_CASE_P(4, uint32_t, 12, 4, 1, 2, 0, 1)
     POLY_CASE_P(8, uint64_t, 12, 4, 1, 1, 3, 0)
     POLY_CASE_P(8, uint64_t, 12, 4, 1, 2, 3, 1)
     POLY_CASE_P(8, uint64_t, 8, 4, 16, 1, 3, 0)
@@ -440,7 +443,7 @@ int emu_slot_ex(int word_bytes, int logn, int logr, int lo, int pl, int tid, int
     const int n = 1 << logn;
     const int e = ((tid >> lo) << (lo + logr)) | (k << lo) | (tid & ((1 << lo) - 1));
     const int E = pl * n + e;
-    if (pad) return E + (E >> 4);   // Cfg::spos, PAD = 1
+    if (pad) return E + (E >> logr);   // Cfg::spos, PAD = 1
     const int mask = (1 << (word_bytes == 4 ? 5 : 4)) - 1;
     return E ^ ((E >> logr) & mask);
 }

@@ -336,3 +336,16 @@ def test_emulated_solinas_transform_domain_kernels(co):
     assert (emu.spectrum(*args, 5).astype(np.uint64) == co.cg_ntt(a, omega, q)).all()
     assert (emu.spectrum(*args, 7).astype(np.uint64) == co.cg_intt(a, omega, q)).all()
     assert emu.lib().emu_range_violations() == 0
+
+
+@pytest.mark.parametrize("logn,logr,ppc,tag", [(8, 4, 16, "dilithium"), (10, 5, 8, "n1024_24"), (12, 4, 1, "n4096_24")])
+def test_emulated_padded_32bit_shapes(logn, logr, ppc, tag, co):
+    p = O.PARAMS[tag]
+    n, q, psi = p["n"], p["q"], p["psi"]
+    rng = np.random.default_rng(logn)
+    a = rng.integers(0, q, size=(ppc + 3, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(ppc + 3, n), dtype=np.uint64)
+    a[0], b[0] = q - 1, q - 1
+    want = co.nwc_poly_mult(a, b, psi, q, threads=4)
+    assert (emu.polymul(4, logn, logr, ppc, 2, 0, a, b, q, psi, pad=1).astype(np.uint64) == want).all()
+    assert emu.lib().emu_range_violations() == 0

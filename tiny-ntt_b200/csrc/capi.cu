@@ -171,6 +171,7 @@ int choose_default_variant(const tntt_plan *p) {
     static const char *prefer[] = {
         "u64_n12_r4_p1_a2_red2_b2_s0_t0_pad", "u64_n12_r4_p1_a2_red1_b2_s0_t0_pad",
         "u64_n12_r4_p1_a1_red1_b3_s1_t0", "u64_n12_r4_p1_a2_red1_b2_s0_t0", "u64_n12_r4_p1_a1_red0_b2_s0_t0",
+        "u32_n12_r4_p1_a2_red0_b3_s0_t0_pad", "u32_n10_r5_p8_a2_red0_b2_s0_t0_pad", "u32_n8_r4_p16_a2_red0_b3_s0_t0_pad",
         "u32_n12_r4_p1_a2_red0_b3_s0_t0", "u32_n10_r5_p8_a2_red0_b2_s0_t0", "u32_n8_r4_p16_a2_red0_b3_s0_t0",
     };
     const std::vector<PolymulVariant> &vs = all_variants();

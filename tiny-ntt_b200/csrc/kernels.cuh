@@ -53,9 +53,11 @@ TNTT_CX int cbitrev(int v, int bits) {   // compile-time bit reversal (register 
 
 // Geometry of one kernel variant: W word, N = 2^LOGN coefficients, R = 2^LOGR per thread,
 // PPC polynomials per CTA, NA operands transformed side by side (sharing twiddle loads).
-// PAD_ = 1 (64-bit words, 16 coefficients per thread): the tile is padded by one word per 16 instead of XOR-swizzled.
-// Slots are then linear in the register index, so an exchange needs one base address per access pattern and
-// immediate offsets (the swizzle costs a LOP3 + LEA per access); still conflict-free for every pattern used.
+// PAD_ = 1: the tile is padded by one word per R instead of XOR-swizzled.  Slots are then linear in the register index
+// for every layout, so an exchange needs one base address per access pattern and immediate offsets (the swizzle costs
+// a LOP3 + LEA per access).  Conflict-free for every pattern of the 64-bit shapes and of the 32-bit N = 256 / 1024
+// shapes; the 32-bit N = 4096 shape pays one two-way conflict in the accesses with the register field at bit 8 and is
+// still 5 % faster (tests/test_layout.py enumerates all of them; profiles/r02_whatif_u32.log).
 template <typename W_, int LOGN_, int LOGR_, int PPC_, int PAD_ = 0> struct Cfg {
     using W = W_;
     static constexpr int PAD = PAD_;
@@ -65,13 +67,14 @@ template <typename W_, int LOGN_, int LOGR_, int PPC_, int PAD_ = 0> struct Cfg 
     static constexpr int NPASS = (LOGN + LOGR - 1) / LOGR;
     static constexpr int BANK_MASK = (1 << WordTraits<W>::BANK_BITS) - 1;
     // the padded shapes run two operands side by side at 128 registers: deeper twiddle groups, shallower store groups
-    static constexpr int TG = kTgOverride ? kTgOverride : (PAD_ ? 8 : 4);
-    static constexpr int POST_GROUP = kPostGroupOverride ? kPostGroupOverride : (PAD_ ? 2 : 4);
+    static constexpr bool WIDE_PAD = PAD_ && sizeof(W_) == 8;
+    static constexpr int TG = kTgOverride ? kTgOverride : (WIDE_PAD ? 8 : 4);
+    static constexpr int POST_GROUP = kPostGroupOverride ? kPostGroupOverride : (WIDE_PAD ? 2 : 4);
     // NA > 1: both operands' CTA-wide regroupings share one pair of barriers (measured: only pays in the padded shapes)
 #ifdef TNTT_MERGE_EXCH
     static constexpr int MERGE_EXCH = TNTT_MERGE_EXCH;   // bit 0: the warp-local exchanges, bit 1: the CTA-wide ones
 #else
-    static constexpr int MERGE_EXCH = PAD_ ? 2 : 0;
+    static constexpr int MERGE_EXCH = WIDE_PAD ? 2 : 0;
 #endif
     // per-thread twiddle tables are prefetched one pass ahead only when they are too big to stay in L1
     #if defined(TNTT_FORCE_PREFETCH)
@@ -93,10 +96,9 @@ template <typename W_, int LOGN_, int LOGR_, int PPC_, int PAD_ = 0> struct Cfg 
         return ((tid >> LO) << (LO + LOGR)) | (k << LO) | (tid & ((1 << LO) - 1));
     }
     // shared-memory slot of CTA-wide element index E (= poly_in_cta * N + coefficient index)
-    static constexpr int TILE = PPC * N + (PAD ? PPC * N / 16 : 0);   // words of one tile
-    static_assert(!PAD || (sizeof(W_) == 8 && LOGR_ == 4), "the padded tile is laid out for 8-byte words, R = 16");
+    static constexpr int TILE = PPC * N + (PAD ? PPC * N / R : 0);   // words of one tile
     static TNTT_HD int spos(int E) {
-        if constexpr (PAD) return E + (E >> 4);
+        if constexpr (PAD) return E + (E >> LOGR);
         else return E ^ ((E >> LOGR) & BANK_MASK);
     }
     // size of the transposed last-forward-pass twiddle table

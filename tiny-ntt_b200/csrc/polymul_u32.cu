@@ -23,6 +23,10 @@ static const PolymulVariant kVariants[] = {
     // three CTAs per SM (80 registers): the four-CTA shapes above spill a little at 64 registers
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 8, 4, 16, 2, 0, 3),
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 12, 4, 1, 2, 0, 3),
+    // round 2: padded tiles (immediate-offset exchanges) for the default shapes of the three shipped 24-bit rings
+    TNTT_POLYMUL_VARIANT_P(uint32_t, 32, 8, 4, 16, 2, 0, 3, 0),
+    TNTT_POLYMUL_VARIANT_P(uint32_t, 32, 10, 5, 8, 2, 0, 2, 0),
+    TNTT_POLYMUL_VARIANT_P(uint32_t, 32, 12, 4, 1, 2, 0, 3, 0),
     // sizes next to the reference's three (other NTT-friendly rings): N = 512, 2048, 8192
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 9, 5, 16, 2, 0, 2),
     TNTT_POLYMUL_VARIANT(uint32_t, 32, 11, 4, 2, 2, 0, 3),

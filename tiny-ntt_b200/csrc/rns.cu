@@ -55,9 +55,9 @@ template <class C, int NA, int RED, int MINB, int STASH = 0> struct RnsInst {
         return cudaGetLastError();
     }
     // the transform-domain kernels hold one operand: one tile, the occupancy of the single-modulus spectrum kernels
-    // (the unpadded tile: its twiddle-group depth is the one tuned for one operand at 80 registers; the spectrum
-    // order depends on R and P only, so it is the order of the single-modulus plans of the same size)
-    using CS = Cfg<W, C::LOGN, C::LOGR, C::PPC, 0>;
+    // (64-bit words: the unpadded tile, whose twiddle-group depth is the one tuned for one operand at 80 registers; the
+    // spectrum order depends on R and P only, so it is the order of the single-modulus plans of the same size)
+    using CS = Cfg<W, C::LOGN, C::LOGR, C::PPC, (sizeof(W) == 4 ? C::PAD : 0)>;
     static constexpr size_t SP_SMEM = (size_t)CS::TILE * sizeof(W);
     static constexpr int SP_MINB = (sizeof(W) == 4 && C::LOGR == 5) ? 2 : (NA == 2 ? MINB + 1 : MINB);
     static cudaError_t spectrum(int op, const void *a, const void *b, void *c, size_t batch, size_t b_stride, const void *limbs,
@@ -98,11 +98,12 @@ const RnsVariant kRnsVariants[] = {
     RNS_VARIANT("rns_u64_n10_r4_p4_a1_red0_b2", uint64_t, 10, 4, 4, 0, 1, 0, 2, 0),
     RNS_VARIANT("rns_u64_n8_r4_p16_a1_red1_b2", uint64_t, 8, 4, 16, 0, 1, 1, 2, 0),
     RNS_VARIANT("rns_u64_n8_r4_p16_a1_red0_b2", uint64_t, 8, 4, 16, 0, 1, 0, 2, 0),
-    RNS_VARIANT("rns_u32_n12_r4_p1_a2_red0_b3", uint32_t, 12, 4, 1, 0, 2, 0, 3, 0),
-    RNS_VARIANT("rns_u32_n12_r4_p1_a2_red0_b2", uint32_t, 12, 4, 1, 0, 2, 0, 2, 0),     // alternatives: TNTT_RNS_PICK=1, 2 (tools/rns_bench.py)
+    RNS_VARIANT("rns_u32_n12_r4_p1_a2_red0_b3_pad", uint32_t, 12, 4, 1, 1, 2, 0, 3, 0),
+    RNS_VARIANT("rns_u32_n12_r4_p1_a2_red0_b3", uint32_t, 12, 4, 1, 0, 2, 0, 3, 0),     // alternatives: TNTT_RNS_PICK=1, 2, 3 (tools/rns_bench.py)
+    RNS_VARIANT("rns_u32_n12_r4_p1_a2_red0_b2", uint32_t, 12, 4, 1, 0, 2, 0, 2, 0),
     RNS_VARIANT("rns_u32_n12_r4_p1_a1_red0_b4", uint32_t, 12, 4, 1, 0, 1, 0, 4, 0),
-    RNS_VARIANT("rns_u32_n10_r5_p8_a2_red0_b2", uint32_t, 10, 5, 8, 0, 2, 0, 2, 0),
-    RNS_VARIANT("rns_u32_n8_r4_p16_a2_red0_b3", uint32_t, 8, 4, 16, 0, 2, 0, 3, 0),
+    RNS_VARIANT("rns_u32_n10_r5_p8_a2_red0_b2_pad", uint32_t, 10, 5, 8, 1, 2, 0, 2, 0),
+    RNS_VARIANT("rns_u32_n8_r4_p16_a2_red0_b3_pad", uint32_t, 8, 4, 16, 1, 2, 0, 3, 0),
 };
 
 // ---------------------------------------------------------------------------------------------

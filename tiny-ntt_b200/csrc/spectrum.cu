@@ -6,7 +6,7 @@ namespace tntt {
 
 template <class C, int RED, int MINB> struct SpectrumInst {
     using W = typename C::W;
-    static constexpr size_t SMEM = (size_t)C::PPC * C::N * sizeof(W);
+    static constexpr size_t SMEM = (size_t)C::TILE * sizeof(W);
     static unsigned ctas(size_t batch) { return (unsigned)((batch + C::PPC - 1) / C::PPC); }
     static cudaError_t forward(const void *in, void *out, size_t batch, const void *tables, const void *mod, cudaStream_t st) {
         spectrum_forward_kernel<C, RED, MINB><<<ctas(batch), C::THREADS, SMEM, st>>>(
@@ -109,22 +109,25 @@ template <class C, int CS, int RED, int MINB> struct SpectrumClusterInst {
             &SpectrumClusterInst<Cfg<WT, LN, LR, 1>, CS, RED, MINB>::prepare, nullptr, nullptr, CS      \
     }
 
-#define TNTT_SPECTRUM_VARIANT(WT, WB, LN, LR, PPC, RED, MINB)                                                \
+#define TNTT_SPECTRUM_VARIANT(WT, WB, LN, LR, PPC, RED, MINB) TNTT_SPECTRUM_VARIANT_X("sp_u" #WB "_n" #LN "_r" #LR "_p" #PPC "_red" #RED, WT, WB, LN, LR, PPC, RED, MINB, 0)
+// padded tile (kernels.cuh, Cfg): the spectrum order depends on R and P only, so it is the same as without padding
+#define TNTT_SPECTRUM_VARIANT_P(WT, WB, LN, LR, PPC, RED, MINB) TNTT_SPECTRUM_VARIANT_X("sp_u" #WB "_n" #LN "_r" #LR "_p" #PPC "_red" #RED "_pad", WT, WB, LN, LR, PPC, RED, MINB, 1)
+#define TNTT_SPECTRUM_VARIANT_X(NAME, WT, WB, LN, LR, PPC, RED, MINB, PAD)                                     \
     SpectrumVariant {                                                                                        \
-        "sp_u" #WB "_n" #LN "_r" #LR "_p" #PPC "_red" #RED, WB / 8, LN, LR, PPC, RED,                          \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::forward,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::inverse,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::polymul,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::prepare,                                   \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::forward_natural,                           \
-            &SpectrumInst<Cfg<WT, LN, LR, PPC>, RED, MINB>::inverse_natural                            \
+        NAME, WB / 8, LN, LR, PPC, RED,                                                                        \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC, PAD>, RED, MINB>::forward,                                      \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC, PAD>, RED, MINB>::inverse,                                      \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC, PAD>, RED, MINB>::polymul,                                      \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC, PAD>, RED, MINB>::prepare,                                      \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC, PAD>, RED, MINB>::forward_natural,                              \
+            &SpectrumInst<Cfg<WT, LN, LR, PPC, PAD>, RED, MINB>::inverse_natural                               \
     }
 
 // one shape per (word, N, reduction mode): the spectrum order is part of the plan, not of a kernel variant
 static const SpectrumVariant kVariants[] = {
-    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 8, 4, 16, 0, 4),
-    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 10, 5, 8, 0, 2),
-    TNTT_SPECTRUM_VARIANT(uint32_t, 32, 12, 4, 1, 0, 4),
+    TNTT_SPECTRUM_VARIANT_P(uint32_t, 32, 8, 4, 16, 0, 4),
+    TNTT_SPECTRUM_VARIANT_P(uint32_t, 32, 10, 5, 8, 0, 2),
+    TNTT_SPECTRUM_VARIANT_P(uint32_t, 32, 12, 4, 1, 0, 4),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 8, 4, 16, 0, 2),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 8, 4, 16, 1, 2),
     TNTT_SPECTRUM_VARIANT(uint64_t, 64, 10, 4, 4, 0, 2),
