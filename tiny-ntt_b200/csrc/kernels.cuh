@@ -79,8 +79,12 @@ template <typename W_, int LOGN_, int LOGR_, int PPC_, int PAD_ = 0> struct Cfg 
     // per-thread twiddle tables are prefetched one pass ahead only when they are too big to stay in L1
     #if defined(TNTT_FORCE_PREFETCH)
     static constexpr bool PREFETCH = true;
+#elif defined(TNTT_X_NO_PREFETCH)
+    static constexpr bool PREFETCH = false;   // what-if only
 #else
-    static constexpr bool PREFETCH = (size_t)N * 2 * sizeof(W) >= 32768;
+    // (64 KB per table and more; the 32 KB tables of the 32-bit N = 4096 shape stay in L1 next to its three tiles, and
+    // prefetching them costs 5 % there: 42.9 -> 45.3 M polymul/s, profiles/r02_whatif_u32.log)
+    static constexpr bool PREFETCH = (size_t)N * 2 * sizeof(W) >= 65536;
 #endif
     static_assert(LOGN >= LOGR, "a thread cannot hold more than the polynomial");
     // forward pass p works on index bits [fwd_lo(p), fwd_bhi(p)), high bits first
