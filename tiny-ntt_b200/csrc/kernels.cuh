@@ -605,7 +605,10 @@ __device__ __forceinline__ void forward_all(typename C::W (&x)[NA][C::R], typena
                 for (int a = 0; a < NA; ++a) exchange<C, C::fwd_lo(PASS - 1), C::fwd_lo(PASS)>(x[a], tile + a * C::TILE, pl, tid);
             }
         }
-        if constexpr (PASS + 2 == C::NPASS && C::PREFETCH && !TMA) prefetch_fwd_last<C>(tid, tb);
+#ifndef TNTT_PF_MASK
+#define TNTT_PF_MASK 7     // which per-thread tables are prefetched one pass ahead: 1 = fwd_last, 2 = last inverse pass, 4 = store table
+#endif
+        if constexpr (PASS + 2 == C::NPASS && C::PREFETCH && !TMA && (TNTT_PF_MASK & 1)) prefetch_fwd_last<C>(tid, tb);
         if constexpr (TMA && PASS + 1 == C::NPASS) {
             if (wait_table) tma->wait();
         }
@@ -649,8 +652,8 @@ __device__ __forceinline__ void dit_all(typename C::W (&x)[C::R], typename C::W 
             else exchange_sync<C, C::inv_lo(PASS - 1), C::inv_lo(PASS)>();
             tile_read<C, C::inv_lo(PASS)>(x, tile, pl, tid);
         }
-        if constexpr (PASS + 2 == C::NPASS && PF && !TMA) prefetch_dit_last<C>(tid, dt.pyr);
-        if constexpr (PASS + 1 == C::NPASS && PF) prefetch_post<C>(tid, post);
+        if constexpr (PASS + 2 == C::NPASS && PF && !TMA && (TNTT_PF_MASK & 2)) prefetch_dit_last<C>(tid, dt.pyr);
+        if constexpr (PASS + 1 == C::NPASS && PF && (TNTT_PF_MASK & 4)) prefetch_post<C>(tid, post);
         if constexpr (TMA && PASS + 1 == C::NPASS) tma->wait();
         if constexpr (APRE) dit_pass<C, PASS, RED, IN_BND, false, false, true>(x, tid, dt, mod, nullptr, tall);
         else dit_pass<C, PASS, RED, IN_BND, TMA, PRE>(x, tid, dt, mod, stab, &t0);
