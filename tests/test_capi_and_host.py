@@ -62,6 +62,15 @@ def test_no_cpu_fallback_without_a_gpu():
     assert rc == -7 and b"no CPU path" in tntt.lib().tntt_last_error()      # TNTT_NO_DEVICE
     v = ctypes.c_double()
     assert tntt.lib().tntt_microbench(0, 0, ctypes.byref(v)) == -7
+    # the round-2 entry points fail the same way: no plan without a device, nothing computes on the host
+    q, psi = (ctypes.c_uint64 * 1)(8380417), (ctypes.c_uint64 * 1)(1239911)
+    rc = tntt.lib().tntt_rns_plan_create(ctypes.byref(h), 0, 256, q, psi, 1)
+    assert rc == -7 and b"no CPU path" in tntt.lib().tntt_last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tntt.RnsContext(256, [8380417], [1239911])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tntt.get_plans(256, 8380417, 1239911)
+    assert tntt.lib().tntt_polymul_host_multi(None, 0, None, None, None, 0) == -1      # TNTT_BAD_ARG: no plans
 
 
 def test_product_never_imports_the_oracle():
