@@ -432,7 +432,9 @@ def run_ours(args):
     # ---- end to end through the host-buffer entry points (pinned memory, H2D + kernel + D2H per step) ------
     e2e = None
     if not args.no_e2e:
-        e_rows = min(rows, 1 << 13) if tag == "n4096_60" else min(rows, (256 << 20) // (n * wb))
+        # one step = the rank's whole shard, as in the device-resident measurement (N = 1: 3 x 1.07 GB of pinned buffers);
+        # under torchrun a quarter of it per GPU, so that rank 0's single-process arena for all GPUs stays small
+        e_rows = rows if world == 1 else min(rows, max(1, (256 << 20) // (n * wb)))
         bytes_row = n * wb
         e_steps = max(3, min(args.steps, 10))
         ha = a[:e_rows].cpu().pin_memory()
