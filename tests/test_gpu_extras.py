@@ -362,6 +362,20 @@ def test_plain_c_client_of_the_transform_domain_entry_points(tmp_path):
     assert "PASS" in out.stdout
 
 
+def test_plain_c_client_of_the_multi_modulus_and_multi_gpu_entry_points(tmp_path):
+    """examples/rns_driver.c: tntt_find_psi, tntt_rns_plan_create (device-generated tables), tntt_rns_polymul,
+    tntt_rns_spectrum_forward + tntt_rns_polymul_spectrum, tntt_polymul_host_multi -- from plain C."""
+    exe = str(tmp_path / "rns_driver")
+    lib = os.path.join(ROOT, "tiny-ntt_b200")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"),
+                           os.path.join(ROOT, "examples", "rns_driver.c"), "-L" + lib, "-ltntt",
+                           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "PASS" in out.stdout and "same bits" in out.stdout
+
+
 # ------------------------------------------------------------------------------------------------
 # multi-modulus engine (csrc/rns.cu): one launch for [L, B, N], tables generated on the device
 # ------------------------------------------------------------------------------------------------
