@@ -493,6 +493,7 @@ def run_ours(args):
         del a, b, c
         torch.cuda.empty_cache()
         others = []
+        from tntt import fixtures
         traffic_db = load_json("traffic.json")
         peaks, _ = measured_peaks()
         peak_lo = None
@@ -507,6 +508,13 @@ def run_ours(args):
             pl = tntt.get_plan(op["n"], op["q"], op["psi"], True, local)
             x, y, z = operands(pl, max(nrows_gpu, 1), 99 + rank)
             active = nrows_gpu > 0
+            if active and rank == 0:      # row 0 = the C++ benchmark's LCG polynomials: the reference's `checksum=` constant
+                odt, osd = (np.uint32, np.int32) if pl.word_bytes == 4 else (np.uint64, np.int64)
+                x[0] = torch.from_numpy(np.array(fixtures.make_poly(1, op["n"], op["q"]), dtype=odt).view(osd)).cuda()
+                y[0] = torch.from_numpy(np.array(fixtures.make_poly(2, op["n"], op["q"]), dtype=odt).view(osd)).cuda()
+                tntt.polymul(pl, x[:1], y[:1], out=z[:1])
+                if fixtures.checksum(z[0].cpu().numpy().view(odt).tolist(), op["q"]) != fixtures.REFERENCE_CHECKSUMS[(op["n"], op["q"])]:
+                    raise SystemExit(f"parity gate failed for {otag}: row-0 checksum differs from the reference binary's")
             fn = (lambda: tntt.polymul(pl, x[:nrows_gpu], y[:nrows_gpu], out=z[:nrows_gpu])) if active else (lambda: None)
             per = max(nrows_gpu, 1) * op["n"] * pl.word_bytes * 3
             reps = int(max(5, min(400, 2e9 / per)))
