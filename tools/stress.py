@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Randomised parity stress: random NTT-friendly primes (24..60 bits), every fused size, random batch sizes,
 every variant and the transform-domain / natural-order routes against the C oracle.  usage: stress.py [SECONDS]"""
+import faulthandler
 import os
 import random
 import sys
@@ -43,8 +44,12 @@ def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rnd = random.Random(2026)
     co = COracle()
-    t0, cases, bigs = time.time(), 0, 0
+    t0, cases, bigs, rns_cases, literal_cases = time.time(), 0, 0, 0, 0
     while time.time() - t0 < budget:
+        # a case that takes longer than two minutes is a hang: dump every thread's stack and give up
+        faulthandler.dump_traceback_later(120, exit=True)
+        if cases % 500 == 0:
+            print(f"[{time.time() - t0:6.1f} s] {cases} cases", file=sys.stderr, flush=True)
         logn = rnd.choice([8, 9, 10, 11, 12, 13, 14, 15])
         n = 1 << logn
         bits = rnd.choice([20, 23, 26, 28, 31, 40, 50, 58, 59, 60])
@@ -103,8 +108,53 @@ def main():
                 assert torch.equal(tntt.inverse(plan, tntt.pointwise(plan, fa, fb), twist=True), c0), ("big batch, twisted", n, q)
             del xa, xb, c0
             bigs += 1
+        # every few cases: a multi-modulus context over random primes of one word class, against the oracle limb by limb
+        if cases % 7 == 0 and logn in (8, 10, 12):
+            L = rnd.choice([1, 2, 5, 16, 17, 20])
+            qs, k0 = [], q
+            while len(qs) < L and k0 > 2 * n:
+                if is_prime(k0):
+                    qs.append(k0)
+                k0 -= 2 * n
+            L = len(qs)
+            try:
+                ctx = tntt.RnsContext(n, qs)
+            except ValueError:
+                ctx = None          # the descending primes straddle a word / reduction class boundary: not a valid context
+            if ctx is not None:
+                r2 = rnd.choice([1, 3, 33])
+                ra = np.stack([rng.integers(0, m, size=(r2, n), dtype=np.uint64) for m in qs])
+                rb = np.stack([rng.integers(0, m, size=(r2, n), dtype=np.uint64) for m in qs])
+                nd, sd = (np.uint32, np.int32) if ctx.word_bytes == 4 else (np.uint64, np.int64)
+                da = torch.from_numpy(ra.astype(nd).view(sd)).cuda()
+                db = torch.from_numpy(rb.astype(nd).view(sd)).cuda()
+                got = ctx.polymul(da, db)
+                assert torch.equal(ctx.polymul_spectrum(da, ctx.forward_spectrum(db)), got), ("rns spectrum", n, qs[0], L)
+                gh = got.cpu().numpy().view(nd).astype(np.uint64)
+                for l, (m, ps) in enumerate(zip(ctx.moduli, ctx.psis)):
+                    assert (gh[l] == co.nwc_poly_mult(ra[l], rb[l], ps, m, threads=8)).all(), ("rns", n, m, L, l)
+                    assert ctx.tables_match_host_generators(l)
+                rns_cases += 1
+                del ctx
+        # ... and a literal plan: a modulus that is no prime (the reference accepts it), small n, against the Python oracle
+        if cases % 11 == 0:
+            from oracle import ntt_oracle as PO
+            ln = rnd.choice([3, 4, 5, 6])
+            m = rnd.randrange(2, 1 << rnd.choice([8, 20, 31, 45, 59])) | rnd.choice([0, 1])
+            w = rnd.randrange(m)
+            lp = tntt.get_plan(1 << ln, m, w, True)
+            xs = [rnd.randrange(m) for _ in range(1 << ln)]
+            ys = [rnd.randrange(m) for _ in range(1 << ln)]
+            nd, sd = (np.uint32, np.int32) if lp.word_bytes == 4 else (np.uint64, np.int64)
+            tx = torch.from_numpy(np.array([xs], dtype=nd).view(sd)).cuda()
+            ty = torch.from_numpy(np.array([ys], dtype=nd).view(sd)).cuda()
+            got = tntt.polymul(lp, tx, ty).cpu().numpy().view(nd).astype(np.uint64)[0].tolist()
+            assert got == PO.nwc_poly_mult(xs, ys, w, m), ("literal", 1 << ln, m, w)
+            literal_cases += 1
         cases += 1
-    print(f"stress ok: {cases} random (n, q, batch) cases ({bigs} with GPU-filling batches) in {time.time() - t0:.0f} s")
+    faulthandler.cancel_dump_traceback_later()
+    print(f"stress ok: {cases} random (n, q, batch) cases ({bigs} with GPU-filling batches, {rns_cases} multi-modulus contexts, "
+          f"{literal_cases} literal plans) in {time.time() - t0:.0f} s")
 
 
 if __name__ == "__main__":
