@@ -376,6 +376,37 @@ def test_plain_c_client_of_the_multi_modulus_and_multi_gpu_entry_points(tmp_path
     assert "PASS" in out.stdout and "same bits" in out.stdout
 
 
+def test_benchmark_cli_prints_the_reference_report(tmp_path, golden_all):
+    """examples/benchmark_ntt_gpu.c: the report of software_benchmark/benchmark_ntt.cpp:286-293 (and the 60-bit build) --
+    same keys in the same order, and the two checksum lines the reference binaries print for each of the four rings,
+    for one row and for a batch; --check compares with the schoolbook product like the reference's."""
+    exe = str(tmp_path / "benchmark_ntt_gpu")
+    lib = os.path.join(ROOT, "tiny-ntt_b200")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"),
+                           os.path.join(ROOT, "examples", "benchmark_ntt_gpu.c"), "-L" + lib, "-ltntt",
+                           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + lib, "-o", exe])
+    keys = ["forward_ntt_total_ns", "forward_ntt_avg_ns", "forward_ntt_checksum", "total_ns", "avg_ns", "checksum"]
+    for tag, g in golden_all.items():
+        for batch in (1, 37):
+            args = [exe, "--check", "--reps", "3", "--n", str(g["n"]), "--q", str(g["q"]), "--psi", str(g["psi"]), "--batch", str(batch)]
+            out = subprocess.run(args, capture_output=True, text=True, timeout=300)
+            assert out.returncode == 0, (tag, out.stdout + out.stderr)
+            lines = out.stdout.strip().splitlines()
+            assert lines[0] == "benchmark_ntt_gpu" and lines[1] == f"N={g['n']} Q={g['q']} reps=3", (tag, lines[:2])
+            assert [l.split("=")[0] for l in lines[2:8]] == keys, (tag, lines)
+            report = dict(l.split("=") for l in lines[2:])
+            assert int(report["checksum"]) == g["cpp_checksums"]["checksum"], tag
+            assert int(report["forward_ntt_checksum"]) == g["cpp_checksums"]["forward_ntt_checksum"], tag
+            assert (len(lines) == 8) == (batch == 1)
+    # the reference's defaults (N=256, Q=8380417) and its usage error
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "N=256 Q=8380417 reps=100" in out.stdout
+    assert f"checksum={golden_all['dilithium']['cpp_checksums']['checksum']}" in out.stdout.splitlines()
+    bad = subprocess.run([exe, "--frobnicate"], capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 2 and bad.stderr.startswith("usage: benchmark [--check] [--reps count]")
+
+
 # ------------------------------------------------------------------------------------------------
 # multi-modulus engine (csrc/rns.cu): one launch for [L, B, N], tables generated on the device
 # ------------------------------------------------------------------------------------------------
