@@ -18,7 +18,7 @@
  *  - A plan's tables are immutable after creation and the device entry points may be called on it from
  *    several host threads / streams.  Two things are NOT thread-safe: tntt_plan_set_default_variant (a
  *    benchmarking knob that rewrites the plan's dispatch fields; call it before sharing the plan) and
- *    tntt_polymul_host, which serialises callers on the plan's one set of staging buffers.
+ *    tntt_polymul_host / tntt_polymul_spectrum_host, which serialise callers on the plan's one set of staging buffers.
  *    One plan per device.  There is NO CPU fallback: without a CUDA device tntt_plan_create fails
  *    with TNTT_NO_DEVICE.
  *  - Return value: 0 = TNTT_OK, negative = error; tntt_last_error() gives a thread-local message.
@@ -163,6 +163,13 @@ int tntt_spectrum_forward(const tntt_plan *plan, const void *in, void *out, size
 int tntt_spectrum_inverse(const tntt_plan *plan, const void *in, void *out, size_t batch, void *cuda_stream);
 int tntt_polymul_spectrum(const tntt_plan *plan, const void *a, const void *b_spectrum, void *c, size_t batch,
                           size_t b_rows, void *cuda_stream);
+/* tntt_polymul_host with the second operand cached: a and c are HOST buffers, b_spectrum is a DEVICE buffer of
+ * b_rows = 1 or batch spectra written by tntt_spectrum_forward (complete before this call: the pipeline runs on the
+ * plan's own streams).  The fixed-key pattern of reports/final-report.tex:571-610 from host memory: one third less
+ * PCIe traffic than tntt_polymul_host and the two directions carry the same load.  Same pipeline, same blocking and
+ * error behaviour; c is bit-identical to tntt_polymul_host(a, b). */
+int tntt_polymul_spectrum_host(tntt_plan *plan, const void *a_host, const void *b_spectrum, size_t b_rows, void *c_host,
+                               size_t batch);
 
 /* Kernel variants of the fused polymul (tile shape, operands side by side, ...), for benchmarking. */
 int tntt_variant_count(void);

@@ -71,6 +71,7 @@ def test_no_cpu_fallback_without_a_gpu():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         tntt.get_plans(256, 8380417, 1239911)
     assert tntt.lib().tntt_polymul_host_multi(None, 0, None, None, None, 0) == -1      # TNTT_BAD_ARG: no plans
+    assert tntt.lib().tntt_polymul_spectrum_host(None, None, None, 1, None, 1) == -1   # TNTT_BAD_ARG: no plan
 
 
 def test_product_never_imports_the_oracle():

@@ -648,10 +648,10 @@ int tntt_polymul(const tntt_plan *p, const void *a, const void *b, void *c, size
     return generic_polymul(p, a, b, c, batch, (cudaStream_t)stream);
 }
 
-int tntt_polymul_host(tntt_plan *p, const void *a, const void *b, void *c, size_t batch) {
-    if (!p || !a || !b || !c) return fail(TNTT_BAD_ARG, "null argument");
-    if (!p->info.has_psi) return fail(TNTT_BAD_ARG, "polymul needs a plan created from psi");
-    if (batch == 0) return TNTT_OK;
+// The host pipeline behind tntt_polymul_host (b_spectrum == nullptr: a and b both come from the host) and
+// tntt_polymul_spectrum_host (b is a spectrum that already lives on the device; b_rows = batch or 1).
+static int polymul_host_pipeline(tntt_plan *p, const void *a, const void *b, const void *b_spectrum, size_t b_rows, void *c,
+                                 size_t batch) {
     DeviceSetter ds(p->info.device);
     std::lock_guard<std::mutex> lock(p->pipe_mu);
     const size_t row_bytes = (size_t)p->info.n * p->info.word_bytes;
@@ -703,8 +703,13 @@ int tntt_polymul_host(tntt_plan *p, const void *a, const void *b, void *c, size_
         cudaStream_t st = p->pipe_stream[slot];
         what = "cudaMemcpyAsync (host to device)";
         if ((e = cudaMemcpyAsync(p->pipe_buf[slot][0], pa + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(p->pipe_buf[slot][1], pb + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        if ((rc = tntt_polymul(p, p->pipe_buf[slot][0], p->pipe_buf[slot][1], p->pipe_buf[slot][2], nr, st)) != TNTT_OK) break;
+        if (b_spectrum) {
+            const char *bs = (const char *)b_spectrum + (b_rows == 1 ? 0 : r0 * row_bytes);
+            if ((rc = tntt_polymul_spectrum(p, p->pipe_buf[slot][0], bs, p->pipe_buf[slot][2], nr, b_rows == 1 ? 1 : nr, st)) != TNTT_OK) break;
+        } else {
+            if ((e = cudaMemcpyAsync(p->pipe_buf[slot][1], pb + r0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+            if ((rc = tntt_polymul(p, p->pipe_buf[slot][0], p->pipe_buf[slot][1], p->pipe_buf[slot][2], nr, st)) != TNTT_OK) break;
+        }
         what = "cudaMemcpyAsync (device to host)";
         if ((e = cudaMemcpyAsync(pc + r0 * row_bytes, p->pipe_buf[slot][2], nr * row_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
         r0 += nr;
@@ -719,6 +724,22 @@ int tntt_polymul_host(tntt_plan *p, const void *a, const void *b, void *c, size_
     if (rc != TNTT_OK) return rc;
     if (e != cudaSuccess) return fail(TNTT_CUDA_ERROR, "%s: %s", what, cudaGetErrorString(e));
     return TNTT_OK;
+}
+
+int tntt_polymul_host(tntt_plan *p, const void *a, const void *b, void *c, size_t batch) {
+    if (!p || !a || !b || !c) return fail(TNTT_BAD_ARG, "null argument");
+    if (!p->info.has_psi) return fail(TNTT_BAD_ARG, "polymul needs a plan created from psi");
+    if (batch == 0) return TNTT_OK;
+    return polymul_host_pipeline(p, a, b, nullptr, 0, c, batch);
+}
+
+int tntt_polymul_spectrum_host(tntt_plan *p, const void *a, const void *b_spectrum, size_t b_rows, void *c, size_t batch) {
+    if (!p || !a || !b_spectrum || !c) return fail(TNTT_BAD_ARG, "null argument");
+    if (!p->info.spectrum) return fail(TNTT_BAD_ARG, "this plan has no transform-domain kernels (tntt_plan_info.spectrum == 0)");
+    if (batch == 0) return TNTT_OK;
+    if (b_rows != 1 && b_rows != batch) return fail(TNTT_BAD_ARG, "b_rows must be 1 or batch");
+    if ((uintptr_t)b_spectrum & 15) return fail(TNTT_BAD_ARG, "b_spectrum must be a 16-byte aligned device pointer");
+    return polymul_host_pipeline(p, a, nullptr, b_spectrum, b_rows, c, batch);
 }
 
 // Single-process multi-GPU form of the same call: plans[i] lives on its own device

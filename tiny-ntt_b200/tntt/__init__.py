@@ -8,7 +8,8 @@ batched tensor API they are built on.
 from . import fixtures  # noqa: F401
 from ._lib import LIB_PATH, SYMBOLS, TnttError, lib  # noqa: F401
 from .ops import (as_tensor, bit_reverse, butterfly_lanes, cg_stage, forward, forward_spectrum, inverse,  # noqa: F401
-                  inverse_spectrum, microbench, pointwise, polymul, polymul_host, polymul_sharded, polymul_spectrum, reduce,
+                  inverse_spectrum, microbench, pointwise, polymul, polymul_host, polymul_sharded, polymul_spectrum, polymul_spectrum_host,
+                  reduce,
                   scale)
 from .plan import Plan, clear_plan_cache, get_plan, get_plans  # noqa: F401
 from .rns import RnsContext, find_psi  # noqa: F401
@@ -18,5 +19,5 @@ __all__ = [
     "Plan", "get_plan", "clear_plan_cache", "forward", "inverse", "pointwise", "polymul", "polymul_host", "cg_stage",
     "bit_reverse", "scale", "reduce", "butterfly_lanes", "microbench", "shard_range", "shard_rows", "TnttError", "lib",
     "RnsContext", "find_psi", "fixtures", "forward_spectrum", "inverse_spectrum", "polymul_spectrum", "polymul_sharded",
-    "get_plans",
+    "get_plans", "polymul_spectrum_host",
 ]

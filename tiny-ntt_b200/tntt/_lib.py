@@ -26,6 +26,7 @@ SYMBOLS = (
     "tntt_rns_plan_kernel", "tntt_rns_plan_table_bytes", "tntt_rns_polymul", "tntt_rns_plan_check_tables",
     "tntt_rns_kernel_attributes", "tntt_find_psi", "tntt_polymul_host_multi",
     "tntt_rns_spectrum_forward", "tntt_rns_spectrum_inverse", "tntt_rns_polymul_spectrum", "tntt_rns_pointwise",
+    "tntt_polymul_spectrum_host",
 )
 
 
@@ -75,6 +76,7 @@ def lib() -> C.CDLL:
     L.tntt_spectrum_forward.argtypes = [vp, vp, vp, sz, vp]
     L.tntt_spectrum_inverse.argtypes = [vp, vp, vp, sz, vp]
     L.tntt_polymul_spectrum.argtypes = [vp, vp, vp, vp, sz, sz, vp]
+    L.tntt_polymul_spectrum_host.argtypes = [vp, vp, vp, sz, vp, sz]
     L.tntt_cg_stage.argtypes = [vp, vp, vp, sz, i, i, vp]
     L.tntt_bit_reverse.argtypes = [vp, vp, vp, sz, vp]
     L.tntt_scale.argtypes = [vp, vp, vp, sz, u64, vp]

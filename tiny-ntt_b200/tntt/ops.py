@@ -153,6 +153,29 @@ def polymul_host(plan: Plan, a, b, out=None):
     return o
 
 
+def polymul_spectrum_host(plan: Plan, a, b_spectrum, out=None):
+    """polymul_host with the second operand cached on the device: ``a`` is a host tensor (pin it), ``b_spectrum`` a
+    CUDA tensor from forward_spectrum with a's number of rows or a single row shared by every row of a; returns a host
+    tensor.  Blocking; bit-identical to polymul_host(a, b)."""
+    import torch
+
+    ta, tb = as_tensor(a), _prep(plan, b_spectrum, "b_spectrum")
+    if ta.is_cuda:
+        raise ValueError("polymul_spectrum_host takes a host tensor for a")
+    if ta.dtype not in plan.torch_dtypes or tb.dtype != ta.dtype:
+        raise TypeError(f"a must be a host tensor with b_spectrum's dtype ({plan.torch_dtypes})")
+    if ta.shape[-1] != plan.n:
+        raise ValueError(f"Expected {plan.n} coefficients")
+    rows, brows = _rows(ta), _rows(tb)
+    if brows != rows and brows != 1:
+        raise ValueError("b_spectrum must have one row or as many rows as a")
+    ta = ta.contiguous()
+    o = _host_out(ta, out)
+    torch.cuda.current_stream(tb.device).synchronize()   # the spectrum must be complete: the pipeline has its own streams
+    check(lib().tntt_polymul_spectrum_host(plan._h, ta.data_ptr(), tb.data_ptr(), brows, o.data_ptr(), rows))
+    return o
+
+
 def _host_out(t, out):
     import torch
 
