@@ -356,32 +356,14 @@ template <class C, int RED> TNTT_HD typename C::W pointwise_product(typename C::
 // ---------------------------------------------------------------------------------------------
 // cyclic decimation-in-time pass (bit-reversed -> natural) over a root's pyramid table
 // ---------------------------------------------------------------------------------------------
-// IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
-template <class C, int PASS, int RED, int IN_BND, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
-TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
-                       const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
+// the butterflies of one DIT stage (index bit B), twiddles fetched TG at a time ahead of their use
+template <class C, int PASS, int RED, int B, bool SMEM_TW, bool PRE, bool ALLPRE>
+TNTT_HD void dit_stage_products(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
+                                const Tw<typename C::W> *stab, const Tw<typename C::W> *pre_t) {
     using W = typename C::W;
     constexpr int LO = C::inv_lo(PASS);
     constexpr int kb = B - LO;
     constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
-    if constexpr (B == 0 && dit_trivial_ok(RED, IN_BND)) {   // twiddle 1: no product at all
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            if constexpr (RED == 3) {
-                trivial_butterfly(x[2 * g], x[2 * g + 1], mod.q);
-                x[2 * g] = csub(x[2 * g], mod.q);
-                x[2 * g + 1] = csub(x[2 * g + 1], mod.q);
-            } else {
-                trivial_butterfly(x[2 * g], x[2 * g + 1], RED == 2 ? mod.q2 : mod.triv_c);
-            }
-        }
-    } else {
-    if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
-        reduce_top_x<C, kb, RED>(x, mod);
-#if !defined(TNTT_X_NO_REDUCE)
-    static_assert(RED == 0 || bound_after_stage(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)) <= 16,
-                  "inverse stage: lazy values could pass 2^BITS");
-#endif
     constexpr int TG = NJ < C::TG ? NJ : C::TG;
 #pragma unroll
     for (int j0 = 0; j0 < NJ; j0 += TG) {
@@ -407,6 +389,75 @@ TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typena
             }
         }
     }
+}
+
+// IN_BND: bound of the transform's input in units of 2^(BITS-4) (only used when RED)
+template <class C, int PASS, int RED, int IN_BND, int B, bool SMEM_TW = false, bool PRE = false, bool ALLPRE = false>
+TNTT_HD void dit_stage(typename C::W (&x)[C::R], int tid, const DitTables<typename C::W> &dt, const Mod<typename C::W> &mod,
+                       const Tw<typename C::W> *stab = nullptr, const Tw<typename C::W> *pre_t = nullptr) {
+    using W = typename C::W;
+    constexpr int LO = C::inv_lo(PASS);
+    constexpr int kb = B - LO;
+    constexpr int NG = C::R >> (kb + 1), NJ = 1 << kb;
+    constexpr bool J0 = RED == 2 && dit2_j0_trivial() && C::LOGR <= 5;   // see dit2_pass0_bounds (modarith.cuh)
+    if constexpr (J0 && PASS == 0) {
+        // Solinas kernels, first pass: per-register bounds, the j = 0 butterflies of every stage are multiplication-free
+        constexpr int G = Growth<W>::G;
+        constexpr RegBounds rb = dit2_pass0_bounds(G, IN_BND, C::LOGR, B);
+        static_assert(dit2_bound_at(G, IN_BND, C::LOGR, B + 1) <= 16, "first inverse pass: lazy values could pass 2^BITS");
+        static_assert(C::R <= MAX_R && C::R <= kMaxR, "the first pass takes its twiddles from the kernel parameters");
+#pragma unroll
+        for (int g = 0; g < NG && B <= kJ0MaxStage; ++g) {   // j = 0: twiddle root^0 = 1
+            const int k0 = g << (kb + 1), k1 = k0 | (1 << kb);
+            const Dit2Step st = dit2_step(true, G, rb.b[k0], rb.b[k1]);
+            if (st.red_y) x[k1] = solinas_reduce(x[k1]);
+            if (st.red_x) x[k0] = solinas_reduce(x[k0]);
+            trivial_butterfly(x[k0], x[k1], (W)(mod.q * (W)st.by));
+        }
+        constexpr int TG = NJ < C::TG ? NJ : C::TG;
+#pragma unroll
+        for (int j0 = 0; j0 < NJ; j0 += TG) {
+            Tw<W> tw[TG];
+#pragma unroll
+            for (int ji = 0; ji < TG; ++ji)
+                if (j0 + ji || B > kJ0MaxStage) tw[ji] = ALLPRE ? pre_t[(1 << kb) - 1 + j0 + ji] : dt.head[(1 << B) + j0 + ji];
+#pragma unroll
+            for (int ji = 0; ji < TG; ++ji) {
+                const int j = j0 + ji;
+                if (!j && B <= kJ0MaxStage) continue;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const int k0 = (g << (kb + 1)) | j, k1 = k0 | (1 << kb);
+                    if (dit2_step(false, G, rb.b[k0], rb.b[k1]).red_x) x[k0] = solinas_reduce(x[k0]);
+                    ct_butterfly(x[k0], x[k1], tw[ji], mod);
+                }
+            }
+        }
+    } else if constexpr (J0) {
+        // later passes: one bound for all registers, continued from the largest one the first pass leaves
+        constexpr int G = Growth<W>::G, bin = dit2_bound_at(G, IN_BND, C::LOGR, B);
+        if constexpr (stage_needs_reduction(RED, G, bin)) reduce_top_x<C, kb, RED>(x, mod);
+        static_assert(bound_after_stage(RED, G, bin) <= 16, "inverse stage: lazy values could pass 2^BITS");
+        dit_stage_products<C, PASS, RED, B, SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
+    } else if constexpr (B == 0 && dit_trivial_ok(RED, IN_BND)) {   // twiddle 1: no product at all
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            if constexpr (RED == 3) {
+                trivial_butterfly(x[2 * g], x[2 * g + 1], mod.q);
+                x[2 * g] = csub(x[2 * g], mod.q);
+                x[2 * g + 1] = csub(x[2 * g + 1], mod.q);
+            } else {
+                trivial_butterfly(x[2 * g], x[2 * g + 1], RED == 2 ? mod.q2 : mod.triv_c);
+            }
+        }
+    } else {
+    if constexpr (stage_needs_reduction(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)))
+        reduce_top_x<C, kb, RED>(x, mod);
+#if !defined(TNTT_X_NO_REDUCE)
+    static_assert(RED == 0 || bound_after_stage(RED, Growth<W>::G, dit_bound_at(RED, Growth<W>::G, IN_BND, B)) <= 16,
+                  "inverse stage: lazy values could pass 2^BITS");
+#endif
+    dit_stage_products<C, PASS, RED, B, SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
     }
     if constexpr (B + 1 < C::inv_bhi(PASS)) dit_stage<C, PASS, RED, IN_BND, B + 1, SMEM_TW, PRE, ALLPRE>(x, tid, dt, mod, stab, pre_t);
 }

@@ -297,6 +297,58 @@ TNTT_CX int dit_bound_at(int red, int g, int b0, int stage) {
     return b;
 }
 
+// RED 2 only (full reductions are three instructions there): the first DIT pass keeps index bits 0 .. LOGR-1 in the
+// register index, so in EVERY stage of that pass the butterflies with twiddle index j = 0 multiply by root^0 = 1 and
+// the choice is made at compile time -- (x, y) <- (x + y, x - y + c) with c = bound(y) q instead of a product.
+// Such a butterfly doubles a bound instead of adding G, so this pass is tracked per register (units of q); an input
+// is reduced first where its butterfly's outputs could pass 16 units.  Up to 4 + 2 + 1 products per thread fewer (R = 16).
+#if defined(TNTT_NO_J0_TRIVIAL)
+TNTT_CX bool dit2_j0_trivial() { return false; }
+#else
+TNTT_CX bool dit2_j0_trivial() { return true; }
+#endif
+// Measured on B200 (profiles/r02_whatif_j0.log, N = 4096 / 60-bit fused kernel): stages 0-1 (4 products fewer per
+// thread) 13.53 -> 13.68 M polymul/s; stages 0-2 the same (2 products fewer, 2 reductions more); all four stages 13.61
+// (3 reductions more and 8 bytes of spills at 128 registers).  Hence the shortcut stops after stage 1.
+#if defined(TNTT_J0_MAXB)
+constexpr int kJ0MaxStage = TNTT_J0_MAXB;   // experiments: only stages 0 .. TNTT_J0_MAXB take the shortcut
+#else
+constexpr int kJ0MaxStage = 1;
+#endif
+constexpr int kMaxR = 32;
+struct RegBounds { int b[kMaxR]; };
+struct Dit2Step { int bx, by; bool red_x, red_y; };   // bounds entering the butterfly after the reductions it needs
+TNTT_CX Dit2Step dit2_step(bool trivial, int g, int bx, int by) {
+    Dit2Step s{bx, by, false, false};
+    if (trivial) {
+        if (s.bx + s.by > 16) { s.by = 2; s.red_y = true; }
+        if (s.bx + s.by > 16) { s.bx = 2; s.red_x = true; }
+    } else if (s.bx + g > 16) { s.bx = 2; s.red_x = true; }
+    return s;
+}
+// bounds of the 2^logr registers of a thread ENTERING stage `stage` (0 .. logr) of the first DIT pass, inputs below b0
+TNTT_CX RegBounds dit2_pass0_bounds(int g, int b0, int logr, int stage) {
+    RegBounds r{};
+    for (int k = 0; k < (1 << logr); ++k) r.b[k] = b0;
+    for (int B = 0; B < stage; ++B)
+        for (int k0 = 0; k0 < (1 << logr); ++k0) {
+            if (k0 & (1 << B)) continue;
+            const int k1 = k0 | (1 << B);
+            const bool trivial = (k0 & ((1 << B) - 1)) == 0 && B <= kJ0MaxStage;
+            const Dit2Step s = dit2_step(trivial, g, r.b[k0], r.b[k1]);
+            r.b[k0] = r.b[k1] = trivial ? s.bx + s.by : s.bx + g;
+        }
+    return r;
+}
+// uniform bound entering stage `stage` of a RED 2 DIT transform whose first pass holds `logr` stages
+TNTT_CX int dit2_bound_at(int g, int b0, int logr, int stage) {
+    const RegBounds r = dit2_pass0_bounds(g, b0, logr, stage < logr ? stage : logr);
+    int b = 0;
+    for (int k = 0; k < (1 << logr); ++k) b = r.b[k] > b ? r.b[k] : b;
+    for (int s = logr; s < stage; ++s) b = bound_after_stage(2, g, b);
+    return b;
+}
+
 // Montgomery product x*y*2^-BITS mod q, result < x*y/2^BITS + q.
 TNTT_HD uint32_t mont_mul(uint32_t x, uint32_t y, const Mod<uint32_t> &m) {
     const uint64_t p = (uint64_t)x * y;
