@@ -42,6 +42,9 @@ def lib():
         L.emu_is_prime.argtypes = [C.c_uint64]
         L.emu_range_violations.restype = C.c_longlong
         L.emu_lazy_full_ok.argtypes = [C.c_int, C.c_uint64, C.c_int]
+        L.emu_dit2_pass0_bounds.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int)]
+        L.emu_dit2_bound_at.argtypes = [C.c_int] * 4
+        L.emu_dit2_step.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int)]
         _lib = L
     return _lib
 

@@ -462,6 +462,19 @@ uint32_t emu_barrett32(uint32_t x, uint32_t y, uint32_t q) { return barrett_mul(
 uint64_t emu_csub_top64(uint64_t x, uint64_t q) { return csub_top(x, host::make_mod<uint64_t>(q).top_sub); }
 long long emu_range_violations(void) { return tntt::g_range_violations; }
 int emu_is_prime(uint64_t n) { return host::is_prime(n); }
+// the per-register bound tracker of the Solinas kernels' first inverse pass (modarith.cuh): bounds entering `stage`, the
+// uniform bound every later stage starts from, the decisions of one butterfly, and the last stage that takes the shortcut
+void emu_dit2_pass0_bounds(int g, int b0, int logr, int stage, int *out) {
+    const RegBounds r = dit2_pass0_bounds(g, b0, logr, stage);
+    for (int k = 0; k < (1 << logr); ++k) out[k] = r.b[k];
+}
+int emu_dit2_bound_at(int g, int b0, int logr, int stage) { return dit2_bound_at(g, b0, logr, stage); }
+int emu_dit2_step(int trivial, int g, int bx, int by, int *out4) {
+    const Dit2Step s = dit2_step(trivial != 0, g, bx, by);
+    out4[0] = s.bx; out4[1] = s.by; out4[2] = s.red_x; out4[3] = s.red_y;
+    return 0;
+}
+int emu_dit2_j0_max_stage(void) { return dit2_j0_trivial() ? kJ0MaxStage : -1; }
 int emu_lazy_full_ok(int word_bytes, uint64_t q, int logn) {
     return word_bytes == 4 ? host::lazy_full_ok<uint32_t>(q, logn) : host::lazy_full_ok<uint64_t>(q, logn);
 }

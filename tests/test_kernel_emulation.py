@@ -349,3 +349,53 @@ def test_emulated_padded_32bit_shapes(logn, logr, ppc, tag, co):
     want = co.nwc_poly_mult(a, b, psi, q, threads=4)
     assert (emu.polymul(4, logn, logr, ppc, 2, 0, a, b, q, psi, pad=1).astype(np.uint64) == want).all()
     assert emu.lib().emu_range_violations() == 0
+
+
+def test_solinas_first_inverse_pass_bound_tracker_is_sound():
+    """dit2_pass0_bounds / dit2_step (csrc/modarith.cuh): the j = 0 butterflies of the first inverse pass skip their product
+    and DOUBLE a lazy bound.  Replay the tracker's own decisions on worst-case numbers -- every register at the top of its
+    tracked range, products at the top of theirs -- and check that nothing reaches 2^64, that the constant added by a
+    product-free butterfly covers its subtrahend, and that the tracked bound really bounds every value."""
+    import ctypes as C
+    L = emu.lib()
+    q, G = SOLINAS_Q, 3
+    max_stage = L.emu_dit2_j0_max_stage()
+    assert max_stage >= 1                      # the shipped setting: stages 0 and 1 (profiles/r02_whatif_j0.log)
+    for logr in (3, 4, 5):
+        R = 1 << logr
+        for b0 in (1, 2):
+            vals = [b0 * q - 1] * R            # largest values the tracker allows at the input (strictly below b0 q)
+            for B in range(logr):
+                bounds = (C.c_int * 32)()
+                L.emu_dit2_pass0_bounds(G, b0, logr, B, bounds)
+                assert all(vals[k] < bounds[k] * q for k in range(R)), (logr, b0, B)
+                for k0 in range(R):
+                    if k0 & (1 << B):
+                        continue
+                    k1 = k0 | (1 << B)
+                    trivial = (k0 & ((1 << B) - 1)) == 0 and B <= max_stage
+                    st = (C.c_int * 4)()
+                    L.emu_dit2_step(int(trivial), G, bounds[k0], bounds[k1], st)
+                    bx, by, red_x, red_y = list(st)
+                    x, y = vals[k0], vals[k1]
+                    if red_x:
+                        x = L.emu_solinas_reduce(x)
+                        assert x < 2 * q and bx == 2
+                    if red_y:
+                        y = L.emu_solinas_reduce(y)
+                        assert y < 2 * q and by == 2
+                    if trivial:
+                        c = by * q
+                        assert y <= c and x + y < 1 << 64 and x + c < 1 << 64
+                        # worst cases of the two outputs: x + y, and x - y + c with the smallest y
+                        vals[k0], vals[k1] = x + y, x + c
+                    else:
+                        # a lazy product is below G q for ANY word y; outputs x + v and x - v + G q
+                        assert x + G * q < 1 << 64
+                        vals[k0], vals[k1] = x + G * q - 1, x + G * q      # v = G q - 1 and v = 0
+            after = (C.c_int * 32)()
+            L.emu_dit2_pass0_bounds(G, b0, logr, logr, after)
+            assert all(vals[k] < after[k] * q for k in range(R)) and max(after[:R]) <= 16
+            assert L.emu_dit2_bound_at(G, b0, logr, logr) == max(after[:R])
+            # later stages continue from that bound with the uniform rule and never pass 16 units either
+            assert all(L.emu_dit2_bound_at(G, b0, logr, s) <= 16 for s in range(logr, 16))
